@@ -864,10 +864,11 @@ static v3 raycast(const render_ctx *rc, ray r, orc_counters *cn)
 static inline uint8_t to_w8(float s255)
 {
     if (s255 != s255) return 0;
-    double f = floor((double)s255);
-    int64_t w = (int64_t)f;
-    uint8_t b = (uint8_t)((uint64_t)w & 0xff);
-    return b < 255 ? b : 255;
+    float f = floorf(s255);
+    /* |f| >= 2^32 (or inf): the Integer is a multiple of 256 -> 0 */
+    int64_t w = fabsf(f) < 9.0e18f ? (int64_t)f : 0;
+    uint32_t b = (uint32_t)((uint64_t)w & 0xff);
+    return (uint8_t)(b < 255 ? b : 255);
 }
 static void tone_map(v3 c, int trig, uint8_t *out)
 {

@@ -1,0 +1,691 @@
+// sqt_backend.cu -- sm_100a kernels and the C ABI (include/sqt.h) of the squigly-trace B200 backend.
+//
+// Kernels
+//   k_intersect_batch  : one lane per ray, grid-stride; batched Scene.intersect (Geometry.hs:64 / BIH.hs:101)
+//   k_primary          : one lane per pixel; makeRay (Lib.hs:107-114) + closest hit, cached per pixel
+//   k_paths            : persistent lanes, dynamic pixel fetch, path regeneration (sqt_paths.cuh)
+//   k_raycast          : --cast mode (Lib.hs:141-151)
+//   k_tonemap          : mean + rgbFloatToPixelRGB (Lib.hs:88-104)
+//   k_fp32_peak, k_l2_read : roofline denominators measured on the device
+// Host side: context, scene upload (derives the 48-byte branch records from the 16-byte boundary nodes),
+// NCCL group (dlopen'ed), CUDA-event timing of every launch.
+//
+// There is no CPU fallback in this file: every entry point needs a compute-capability-10.x device.
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sqt.h"
+#include "sqt_paths.cuh"
+#include "sqt_layout.hpp"
+
+namespace cg = cooperative_groups;
+using namespace sqt;
+
+// =============================================================================== kernels
+struct DeviceStats {
+    unsigned long long rays, samples, primary_reused;
+    unsigned long long branch_visits, child_box_tests, tri_tests;
+    unsigned long long work_next;       // dynamic work counter of k_paths
+    unsigned long long pad;
+};
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// every lane of the block must call this (full warps)
+__device__ __forceinline__ void flush_stats(DeviceStats *ds, const PathStats &st, const Counters &cn, bool count) {
+    unsigned long long r = warp_sum(st.rays), s = warp_sum(st.samples), p = warp_sum(st.primary_reused);
+    unsigned long long b = 0, c = 0, t = 0;
+    if (count) { b = warp_sum(cn.branch_visits); c = warp_sum(cn.child_box_tests); t = warp_sum(cn.tri_tests); }
+    if ((threadIdx.x & 31) == 0) {
+        if (r) atomicAdd(&ds->rays, r);
+        if (s) atomicAdd(&ds->samples, s);
+        if (p) atomicAdd(&ds->primary_reused, p);
+        if (count) { atomicAdd(&ds->branch_visits, b); atomicAdd(&ds->child_box_tests, c); atomicAdd(&ds->tri_tests, t); }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_intersect_batch(SceneView sc, const float *__restrict__ org,
+                                                         const float *__restrict__ dir, long long n,
+                                                         int *__restrict__ tri_out, float *__restrict__ dist_out,
+                                                         float *__restrict__ point_out, DeviceStats *ds) {
+    Counters cn = {0, 0, 0, 0};
+    PathStats st = {0, 0, 0};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Ray r;
+        r.ox = org[3 * i]; r.oy = org[3 * i + 1]; r.oz = org[3 * i + 2];
+        r.dx = dir[3 * i]; r.dy = dir[3 * i + 1]; r.dz = dir[3 * i + 2];
+        const Hit h = traverse<COUNT>(sc, r, &cn);
+        st.rays += 1;
+        int orig = -1;
+        if (h.tri >= 0) orig = (int)f2u(SQT_LDG4(sc.tris + 3 * (size_t)h.tri + 2).z);
+        tri_out[i] = orig;
+        if (dist_out) dist_out[i] = h.tri >= 0 ? h.dist : 0.0f;
+        if (point_out) {
+            const bool hit = h.tri >= 0;
+            point_out[3 * i] = hit ? XADD(r.ox, XMUL(h.t, r.dx)) : 0.0f;
+            point_out[3 * i + 1] = hit ? XADD(r.oy, XMUL(h.t, r.dy)) : 0.0f;
+            point_out[3 * i + 2] = hit ? XADD(r.oz, XMUL(h.t, r.dz)) : 0.0f;
+        }
+    }
+    flush_stats(ds, st, cn, COUNT);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_primary(SceneView sc, RenderParams p, int2 *__restrict__ prim, DeviceStats *ds) {
+    Counters cn = {0, 0, 0, 0};
+    PathStats st = {0, 0, 0};
+    const long long nwork = work_items(p);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += stride) {
+        const long long pixel = work_to_pixel(p, w);
+        if (pixel < 0) continue;
+        const int y = (int)(pixel / p.cols), x = (int)(pixel % p.cols);
+        const Ray r = make_ray(p, y, x);
+        const Hit h = traverse<COUNT>(sc, r, &cn);
+        st.rays += 1;
+        prim[pixel] = make_int2(h.tri, (int)f2u(h.t));
+    }
+    flush_stats(ds, st, cn, COUNT);
+}
+
+struct DeviceFetch {
+    unsigned long long *counter;
+    long long n;
+    __device__ __forceinline__ long long operator()() {
+        // warp-aggregated claim: one atomic per group of lanes that need work at the same time
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned long long base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(counter, (unsigned long long)g.size());
+        base = g.shfl(base, 0);
+        const long long w = (long long)(base + g.thread_rank());
+        return w < n ? w : -1;
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, const int2 *__restrict__ prim,
+                                               float *__restrict__ accum, DeviceStats *ds) {
+    Counters cn = {0, 0, 0, 0};
+    PathStats st = {0, 0, 0};
+    DeviceFetch fetch = {&ds->work_next, work_items(p)};
+    render_lane<COUNT>(sc, p, prim, accum, fetch, &cn, st);
+    __syncwarp();
+    flush_stats(ds, st, cn, COUNT);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_raycast(SceneView sc, RenderParams p, float *__restrict__ accum, DeviceStats *ds) {
+    Counters cn = {0, 0, 0, 0};
+    PathStats st = {0, 0, 0};
+    const long long nwork = work_items(p);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += stride) {
+        const long long pixel = work_to_pixel(p, w);
+        if (pixel >= 0) raycast_pixel<COUNT>(sc, p, pixel, accum, &cn, st);
+    }
+    flush_stats(ds, st, cn, COUNT);
+}
+
+// avg = (1 / fromIntegral sampleCount) *^ sum outcomes ; rgbFloatToPixelRGB avg   (Lib.hs:88-89)
+__global__ void __launch_bounds__(256) k_tonemap(const float *__restrict__ accum, long long npix, float inv_spp,
+                                                 uint8_t *__restrict__ rgb8) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    uint8_t o[3];
+    tone_map(XMUL(inv_spp, accum[3 * i]), XMUL(inv_spp, accum[3 * i + 1]), XMUL(inv_spp, accum[3 * i + 2]), o);
+    rgb8[3 * i] = o[0]; rgb8[3 * i + 1] = o[1]; rgb8[3 * i + 2] = o[2];
+}
+
+// Non-fused FP32 issue rate: 16 independent chains per lane, alternating FMUL / FADD (the op mix of the
+// bit-exact intersection path, where FMA contraction is forbidden).
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float a, float b) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) { x[i] = __fmul_rn(x[i], a); x[i + 1] = __fadd_rn(x[i + 1], b); }
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) { x[i] = __fadd_rn(x[i], b); x[i + 1] = __fmul_rn(x[i + 1], a); }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 123.456f) out[0] = s;      // keep the chains alive
+}
+
+// L2-resident 128-bit read bandwidth: every block sweeps the same `n4`-element buffer `reps` times.
+__global__ void __launch_bounds__(256) k_l2_read(const float4 *__restrict__ buf, long long n4, int reps, float *out) {
+    float s = 0.0f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int r = 0; r < reps; ++r)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            float4 v;
+            asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(buf + i));
+            s += v.x + v.y + v.z + v.w;
+        }
+    if (s == 123.456f) out[0] = s;
+}
+
+// ============================================================================== NCCL (dlopen)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+static NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return &api;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    for (const char *n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+    if (!api.lib) { api.err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return &api; }
+#define SQT_SYM(field, name) *(void **)(&api.field) = dlsym(api.lib, name); if (!api.field) { api.err = "NCCL symbol missing: " name; api.lib = nullptr; return &api; }
+    SQT_SYM(GetUniqueId, "ncclGetUniqueId") SQT_SYM(CommInitRank, "ncclCommInitRank") SQT_SYM(CommInitAll, "ncclCommInitAll")
+    SQT_SYM(CommDestroy, "ncclCommDestroy") SQT_SYM(Reduce, "ncclReduce") SQT_SYM(GroupStart, "ncclGroupStart")
+    SQT_SYM(GroupEnd, "ncclGroupEnd") SQT_SYM(GetErrorString, "ncclGetErrorString")
+#undef SQT_SYM
+    return &api;
+}
+static const int kNcclFloat32 = 7, kNcclSum = 0;
+
+// ============================================================================== context
+struct sqt_ctx {
+    int device = 0, sm_count = 0, cc_major = 0, cc_minor = 0;
+    char name[128] = {0};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    // scene
+    bool has_scene = false;
+    SceneView sc = {};
+    float4 *d_nodes = nullptr, *d_tris = nullptr, *d_mats = nullptr;
+    int terminate_on_black_ok = 0;
+    uint32_t tree_height = 0;
+    // image buffers
+    long long cap_pixels = 0;
+    int2 *d_prim = nullptr;
+    float *d_accum = nullptr;
+    uint8_t *d_rgb8 = nullptr;
+    long long img_pixels = 0;
+    int img_spp = 0;
+    DeviceStats *d_stats = nullptr;
+    DeviceStats *h_stats = nullptr;     // pinned
+    // batch staging
+    long long cap_rays = 0;
+    float *d_org = nullptr, *d_dir = nullptr, *d_dist = nullptr, *d_point = nullptr;
+    int *d_tri = nullptr;
+    // pinned host staging for image I/O
+    uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
+    // group
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(sqt_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, SQT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+extern "C" int sqt_abi_version(void) { return SQT_ABI_VERSION; }
+
+extern "C" const char *sqt_last_error(const sqt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int sqt_create(int device, sqt_ctx **out) {
+    sqt_ctx *ctx = nullptr;      // for CU(): errors before the context exists go to the thread-local slot
+    if (!out) return fail(nullptr, SQT_E_INVALID, "sqt_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, SQT_E_NO_DEVICE, "no CUDA device (%s); this backend has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, SQT_E_INVALID, "device %d out of range (have %d)", device, n);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, SQT_E_NO_DEVICE, "device %d (%s) is compute capability %d.%d; this library is built for sm_100a only",
+                    device, prop.name, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+    sqt_ctx *c = new sqt_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount; c->cc_major = prop.major; c->cc_minor = prop.minor;
+    snprintf(c->name, sizeof c->name, "%s", prop.name);
+    ctx = c;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
+    CU(cudaMalloc(&c->d_stats, sizeof(DeviceStats)));
+    CU(cudaMallocHost(&c->h_stats, sizeof(DeviceStats)));
+    *out = c;
+    return SQT_OK;
+}
+
+static void free_scene(sqt_ctx *c) {
+    cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_mats);
+    c->d_nodes = c->d_tris = c->d_mats = nullptr; c->has_scene = false;
+}
+
+extern "C" int sqt_destroy(sqt_ctx *c) {
+    if (!c) return SQT_OK;
+    cudaSetDevice(c->device);
+    if (c->comm && nccl_api()->lib) nccl_api()->CommDestroy(c->comm);
+    free_scene(c);
+    cudaFree(c->d_prim); cudaFree(c->d_accum); cudaFree(c->d_rgb8); cudaFree(c->d_stats);
+    cudaFree(c->d_org); cudaFree(c->d_dir); cudaFree(c->d_dist); cudaFree(c->d_point); cudaFree(c->d_tri);
+    cudaFreeHost(c->h_stats); cudaFreeHost(c->h_rgb8); cudaFreeHost(c->h_accum);
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SQT_OK;
+}
+
+extern "C" int sqt_device_info(sqt_ctx *c, int *sm_count, int *cc_major, int *cc_minor, char name_out[128]) {
+    if (!c) return SQT_E_INVALID;
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (name_out) snprintf(name_out, 128, "%s", c->name);
+    return SQT_OK;
+}
+
+// ------------------------------------------------------------------------------ scene upload
+// Walks the boundary tree once (iteratively), validating it and deriving for every Branch the box
+// intersectBIH' would receive for it: the root gets `bounds`, a left child gets its parent's box with
+// hi[axis] := lmax, a right child the parent's box with lo[axis] := rmin (BIH.hs:130-141).
+extern "C" int sqt_upload_scene(sqt_ctx *ctx, const sqt_scene_desc *s) {
+    if (!ctx || !s) return SQT_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    DeviceLayout lay;
+    std::string lerr;
+    const int lrc = build_device_layout(*s, lay, lerr);
+    if (lrc) return fail(ctx, lrc, "%s", lerr.c_str());
+    std::vector<float4> &dn = lay.nodes;
+    std::vector<float4> &dm = lay.mats;
+    const uint32_t n_br = lay.n_branches, height = lay.height;
+    const int tob = lay.terminate_on_black_ok;
+
+    free_scene(ctx);
+    CU(cudaMalloc(&ctx->d_nodes, dn.size() * sizeof(float4)));
+    CU(cudaMalloc(&ctx->d_tris, (size_t)(s->n_tris ? s->n_tris : 1) * 48));
+    CU(cudaMalloc(&ctx->d_mats, dm.size() * sizeof(float4)));
+    CU(cudaMemcpyAsync(ctx->d_nodes, dn.data(), dn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    if (s->n_tris) CU(cudaMemcpyAsync(ctx->d_tris, s->tris, (size_t)s->n_tris * 48, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_mats, dm.data(), dm.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    SceneView v = {};
+    v.nodes = ctx->d_nodes; v.tris = ctx->d_tris; v.mats = ctx->d_mats;
+    for (int k = 0; k < 3; ++k) { v.root_lo[k] = s->root_bounds[k]; v.root_hi[k] = s->root_bounds[3 + k]; }
+    v.n_branches = n_br; v.n_tris = s->n_tris; v.n_mats = s->n_mats;
+    v.root_is_leaf = (s->nodes[0].b & SQT_NODE_LEAF) ? 1u : 0u;
+    ctx->sc = v; ctx->has_scene = true; ctx->terminate_on_black_ok = tob; ctx->tree_height = height;
+    return SQT_OK;
+}
+
+// ------------------------------------------------------------------------------ helpers
+static int ensure_image(sqt_ctx *ctx, long long npix) {
+    if (npix <= ctx->cap_pixels) return SQT_OK;
+    cudaFree(ctx->d_prim); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgb8);
+    ctx->d_prim = nullptr; ctx->d_accum = nullptr; ctx->d_rgb8 = nullptr; ctx->cap_pixels = 0;
+    CU(cudaMalloc(&ctx->d_prim, (size_t)npix * sizeof(int2)));
+    CU(cudaMalloc(&ctx->d_accum, (size_t)npix * 3 * sizeof(float)));
+    CU(cudaMalloc(&ctx->d_rgb8, (size_t)npix * 3));
+    ctx->cap_pixels = npix;
+    return SQT_OK;
+}
+static int ensure_host_image(sqt_ctx *ctx, long long npix) {
+    if (npix <= ctx->cap_host_pixels) return SQT_OK;
+    cudaFreeHost(ctx->h_rgb8); cudaFreeHost(ctx->h_accum); ctx->h_rgb8 = nullptr; ctx->h_accum = nullptr; ctx->cap_host_pixels = 0;
+    CU(cudaMallocHost(&ctx->h_rgb8, (size_t)npix * 3));
+    CU(cudaMallocHost(&ctx->h_accum, (size_t)npix * 3 * sizeof(float)));
+    ctx->cap_host_pixels = npix;
+    return SQT_OK;
+}
+static int ensure_rays(sqt_ctx *ctx, long long n) {
+    if (n <= ctx->cap_rays) return SQT_OK;
+    cudaFree(ctx->d_org); cudaFree(ctx->d_dir); cudaFree(ctx->d_dist); cudaFree(ctx->d_point); cudaFree(ctx->d_tri);
+    ctx->d_org = ctx->d_dir = ctx->d_dist = ctx->d_point = nullptr; ctx->d_tri = nullptr; ctx->cap_rays = 0;
+    CU(cudaMalloc(&ctx->d_org, (size_t)n * 12)); CU(cudaMalloc(&ctx->d_dir, (size_t)n * 12));
+    CU(cudaMalloc(&ctx->d_dist, (size_t)n * 4)); CU(cudaMalloc(&ctx->d_point, (size_t)n * 12));
+    CU(cudaMalloc(&ctx->d_tri, (size_t)n * 4));
+    ctx->cap_rays = n;
+    return SQT_OK;
+}
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// ------------------------------------------------------------------------------ intersect_batch
+extern "C" int sqt_intersect_batch(sqt_ctx *ctx, const float *org, const float *dir, int64_t n, int32_t *tri_out,
+                                   float *dist_out, float *point_out, sqt_stats *stats) {
+    if (!ctx) return SQT_E_INVALID;
+    if (!ctx->has_scene) return fail(ctx, SQT_E_NO_SCENE, "sqt_intersect_batch before sqt_upload_scene");
+    if (n < 0 || (n > 0 && (!org || !dir || !tri_out))) return fail(ctx, SQT_E_INVALID, "bad batch arguments");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n == 0) return SQT_OK;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_rays(ctx, n); if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CU(cudaEventRecord(ctx->ev[0], st));
+    CU(cudaMemcpyAsync(ctx->d_org, org, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_dir, dir, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+    const int block = 256;
+    long long want = (n + block - 1) / block, cap = (long long)ctx->sm_count * 16;
+    const int grid = (int)(want < cap ? want : cap);
+    if (stats)      // instrumented variant: fills the visit/test counters
+        k_intersect_batch<true><<<grid, block, 0, st>>>(ctx->sc, ctx->d_org, ctx->d_dir, n, ctx->d_tri, dist_out ? ctx->d_dist : nullptr,
+                                                        point_out ? ctx->d_point : nullptr, ctx->d_stats);
+    else
+        k_intersect_batch<false><<<grid, block, 0, st>>>(ctx->sc, ctx->d_org, ctx->d_dir, n, ctx->d_tri, dist_out ? ctx->d_dist : nullptr,
+                                                         point_out ? ctx->d_point : nullptr, ctx->d_stats);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[2], st));
+    CU(cudaMemcpyAsync(tri_out, ctx->d_tri, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (dist_out) CU(cudaMemcpyAsync(dist_out, ctx->d_dist, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (point_out) CU(cudaMemcpyAsync(point_out, ctx->d_point, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev[3], st));
+    CU(cudaStreamSynchronize(st));
+    if (stats) {
+        stats->h2d_ms = ev_ms(ctx->ev[0], ctx->ev[1]); stats->device_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+        stats->d2h_ms = ev_ms(ctx->ev[2], ctx->ev[3]);
+        stats->rays_traced = ctx->h_stats->rays; stats->rays_reference = ctx->h_stats->rays;
+        stats->branch_visits = ctx->h_stats->branch_visits; stats->child_box_tests = ctx->h_stats->child_box_tests;
+        stats->tri_tests = ctx->h_stats->tri_tests;
+        stats->h2d_bytes = (uint64_t)n * 24; stats->d2h_bytes = (uint64_t)n * (4 + (dist_out ? 4 : 0) + (point_out ? 12 : 0));
+        stats->kernel_launches = 1;
+    }
+    return SQT_OK;
+}
+
+// ------------------------------------------------------------------------------ render
+static int check_params(sqt_ctx *ctx, const sqt_camera *cam, const sqt_render_params *p) {
+    if (!cam || !p) return fail(ctx, SQT_E_INVALID, "cam/params is NULL");
+    if (!ctx->has_scene) return fail(ctx, SQT_E_NO_SCENE, "sqt_render before sqt_upload_scene");
+    if (p->rows <= 0 || p->cols <= 0 || p->xdiv <= 0 || p->ydiv <= 0 || p->spp <= 0)
+        return fail(ctx, SQT_E_INVALID, "rows/cols/xdiv/ydiv/spp must be positive");
+    if (p->max_depth < 1 || p->max_depth > SQT_MAX_DEPTH) return fail(ctx, SQT_E_UNSUPPORTED, "max_depth must be in 1..%d", SQT_MAX_DEPTH);
+    if (p->mode != 0 && p->mode != 1) return fail(ctx, SQT_E_INVALID, "mode must be 0 (trace) or 1 (cast)");
+    if ((long long)p->rows * p->cols > (1ll << 31)) return fail(ctx, SQT_E_UNSUPPORTED, "image too large");
+    return SQT_OK;
+}
+
+static RenderParams to_device_params(const sqt_ctx *ctx, const sqt_camera *cam, const sqt_render_params *p) {
+    RenderParams d = {};
+    d.rows = p->rows; d.cols = p->cols; d.xdiv = p->xdiv; d.ydiv = p->ydiv; d.seed_stride = p->seed_stride;
+    d.spp = p->spp; d.max_depth = p->max_depth; d.mode = p->mode; d.seed = p->seed;
+    d.rank = ctx->rank; d.world = ctx->world; d.split_samples = (p->flags & SQT_F_SPLIT_SAMPLES) ? 1 : 0;
+    d.primary_reuse = (p->flags & SQT_F_NO_PRIMARY_REUSE) ? 0 : 1;
+    for (int k = 0; k < 3; ++k) d.cam_pos[k] = cam->position[k];
+    for (int k = 0; k < 9; ++k) d.cam_rot[k] = cam->rotation[k];
+    d.terminate_on_black = (ctx->terminate_on_black_ok && !(p->flags & SQT_F_NO_EARLY_TERMINATION)) ? 1 : 0;
+    return d;
+}
+
+// Enqueue all kernels of one render on ctx->stream (no host sync).  Events: 0 start, 1 after primary,
+// 2 after paths, 3 after reduce, 4 after tonemap.
+static int enqueue_render(sqt_ctx *ctx, const RenderParams &d, bool count, uint32_t *launches) {
+    const long long npix = (long long)d.rows * d.cols;
+    int rc = ensure_image(ctx, npix); if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), st));
+    CU(cudaMemsetAsync(ctx->d_accum, 0, (size_t)npix * 3 * sizeof(float), st));
+    CU(cudaEventRecord(ctx->ev[0], st));
+    const long long nwork = work_items(d);
+    uint32_t nl = 0;
+    if (d.mode == 1) {
+        const int block = 256; long long want = (nwork + block - 1) / block, cap = (long long)ctx->sm_count * 16;
+        const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+        CU(cudaEventRecord(ctx->ev[1], st));
+        if (count) k_raycast<true><<<grid, block, 0, st>>>(ctx->sc, d, ctx->d_accum, ctx->d_stats);
+        else k_raycast<false><<<grid, block, 0, st>>>(ctx->sc, d, ctx->d_accum, ctx->d_stats);
+        CU(cudaGetLastError()); nl++;
+    } else {
+        if (d.primary_reuse) {
+            const int block = 256; long long want = (nwork + block - 1) / block, cap = (long long)ctx->sm_count * 16;
+            const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+            if (count) k_primary<true><<<grid, block, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_stats);
+            else k_primary<false><<<grid, block, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_stats);
+            CU(cudaGetLastError()); nl++;
+        }
+        CU(cudaEventRecord(ctx->ev[1], st));
+        // persistent lanes: as many CTAs as stay resident, all of them pulling pixels from one counter
+        int per_sm = 0;
+        if (count) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_paths<true>, 128, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_paths<false>, 128, 0));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)ctx->sm_count * per_sm, want = (nwork + 127) / 128;
+        if (want < grid) grid = want ? want : 1;
+        const int2 *prim = d.primary_reuse ? ctx->d_prim : nullptr;
+        if (count) k_paths<true><<<(int)grid, 128, 0, st>>>(ctx->sc, d, prim, ctx->d_accum, ctx->d_stats);
+        else k_paths<false><<<(int)grid, 128, 0, st>>>(ctx->sc, d, prim, ctx->d_accum, ctx->d_stats);
+        CU(cudaGetLastError()); nl++;
+    }
+    CU(cudaEventRecord(ctx->ev[2], st));
+    if (ctx->world > 1 && ctx->comm) {
+        NcclApi *na = nccl_api();
+        ncclResult_t r = na->Reduce(ctx->d_accum, ctx->d_accum, (size_t)npix * 3, kNcclFloat32, kNcclSum, 0, ctx->comm, st);
+        if (r != 0) return fail(ctx, SQT_E_NCCL, "ncclReduce failed: %s", na->GetErrorString(r));
+        nl++;
+    }
+    CU(cudaEventRecord(ctx->ev[3], st));
+    if (ctx->rank == 0) {
+        const float inv = 1.0f / (float)d.spp;
+        k_tonemap<<<(int)((npix + 255) / 256), 256, 0, st>>>(ctx->d_accum, npix, inv, ctx->d_rgb8);
+        CU(cudaGetLastError()); nl++;
+    }
+    CU(cudaEventRecord(ctx->ev[4], st));
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost, st));
+    ctx->img_pixels = npix; ctx->img_spp = d.spp;
+    *launches = nl;
+    return SQT_OK;
+}
+
+static void fill_stats(sqt_ctx *ctx, sqt_stats *s, uint32_t launches) {
+    if (!s) return;
+    s->primary_ms = ev_ms(ctx->ev[0], ctx->ev[1]); s->paths_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+    s->reduce_ms = ev_ms(ctx->ev[2], ctx->ev[3]); s->tonemap_ms = ev_ms(ctx->ev[3], ctx->ev[4]);
+    s->device_ms = ev_ms(ctx->ev[0], ctx->ev[4]);
+    s->rays_traced = ctx->h_stats->rays; s->samples = ctx->h_stats->samples;
+    s->rays_reference = ctx->h_stats->rays + ctx->h_stats->primary_reused;
+    s->branch_visits = ctx->h_stats->branch_visits; s->child_box_tests = ctx->h_stats->child_box_tests;
+    s->tri_tests = ctx->h_stats->tri_tests;
+    s->kernel_launches = launches;
+}
+
+extern "C" int sqt_render_resident(sqt_ctx *ctx, const sqt_camera *cam, const sqt_render_params *p, sqt_stats *stats) {
+    if (!ctx) return SQT_E_INVALID;
+    int rc = check_params(ctx, cam, p); if (rc) return rc;
+    if (stats) memset(stats, 0, sizeof *stats);
+    CU(cudaSetDevice(ctx->device));
+    const RenderParams d = to_device_params(ctx, cam, p);
+    uint32_t nl = 0;
+    rc = enqueue_render(ctx, d, (p->flags & SQT_F_COUNT_WORK) != 0, &nl); if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    fill_stats(ctx, stats, nl);
+    return SQT_OK;
+}
+
+extern "C" int sqt_download_image(sqt_ctx *ctx, uint8_t *rgb8_out, float *accum_out) {
+    if (!ctx) return SQT_E_INVALID;
+    if (ctx->img_pixels <= 0) return fail(ctx, SQT_E_INVALID, "no rendered image to download");
+    CU(cudaSetDevice(ctx->device));
+    const long long npix = ctx->img_pixels;
+    int rc = ensure_host_image(ctx, npix); if (rc) return rc;
+    if (rgb8_out) CU(cudaMemcpyAsync(ctx->h_rgb8, ctx->d_rgb8, (size_t)npix * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    if (accum_out) CU(cudaMemcpyAsync(ctx->h_accum, ctx->d_accum, (size_t)npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (rgb8_out) memcpy(rgb8_out, ctx->h_rgb8, (size_t)npix * 3);
+    if (accum_out) memcpy(accum_out, ctx->h_accum, (size_t)npix * 12);
+    return SQT_OK;
+}
+
+extern "C" int sqt_render(sqt_ctx *ctx, const sqt_camera *cam, const sqt_render_params *p, uint8_t *rgb8_out,
+                          float *accum_out, sqt_stats *stats) {
+    if (!ctx) return SQT_E_INVALID;
+    int rc = check_params(ctx, cam, p); if (rc) return rc;
+    if (stats) memset(stats, 0, sizeof *stats);
+    CU(cudaSetDevice(ctx->device));
+    const RenderParams d = to_device_params(ctx, cam, p);
+    const long long npix = (long long)d.rows * d.cols;
+    rc = ensure_host_image(ctx, npix); if (rc) return rc;
+    uint32_t nl = 0;
+    rc = enqueue_render(ctx, d, (p->flags & SQT_F_COUNT_WORK) != 0, &nl); if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const bool root = ctx->rank == 0;
+    CU(cudaEventRecord(ctx->ev[5], st));
+    if (root && rgb8_out) CU(cudaMemcpyAsync(ctx->h_rgb8, ctx->d_rgb8, (size_t)npix * 3, cudaMemcpyDeviceToHost, st));
+    if (root && accum_out) CU(cudaMemcpyAsync(ctx->h_accum, ctx->d_accum, (size_t)npix * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev[6], st));
+    CU(cudaStreamSynchronize(st));
+    if (root && rgb8_out) memcpy(rgb8_out, ctx->h_rgb8, (size_t)npix * 3);
+    if (root && accum_out) memcpy(accum_out, ctx->h_accum, (size_t)npix * 12);
+    fill_stats(ctx, stats, nl);
+    if (stats) {
+        stats->d2h_ms = ev_ms(ctx->ev[5], ctx->ev[6]);
+        stats->d2h_bytes = root ? (uint64_t)npix * ((rgb8_out ? 3 : 0) + (accum_out ? 12 : 0)) : 0;
+        stats->h2d_bytes = sizeof(RenderParams);    // camera + parameters travel as kernel arguments
+    }
+    return SQT_OK;
+}
+
+extern "C" int sqt_tone_map(sqt_ctx *ctx, const float *mean_rgb, int64_t npix, uint8_t *rgb8_out) {
+    if (!ctx) return SQT_E_INVALID;
+    if (npix < 0 || (npix > 0 && (!mean_rgb || !rgb8_out))) return fail(ctx, SQT_E_INVALID, "bad tone_map arguments");
+    if (npix == 0) return SQT_OK;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_image(ctx, npix); if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->d_accum, mean_rgb, (size_t)npix * 12, cudaMemcpyHostToDevice, st));
+    k_tonemap<<<(int)((npix + 255) / 256), 256, 0, st>>>(ctx->d_accum, npix, 1.0f, ctx->d_rgb8);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rgb8_out, ctx->d_rgb8, (size_t)npix * 3, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->img_pixels = 0;
+    return SQT_OK;
+}
+
+// ------------------------------------------------------------------------------ group (NCCL)
+extern "C" int sqt_comm_unique_id(uint8_t id_out[SQT_COMM_ID_BYTES]) {
+    NcclApi *na = nccl_api();
+    if (!na->lib) return fail(nullptr, SQT_E_NCCL, "%s", na->err.c_str());
+    ncclUniqueId id;
+    ncclResult_t r = na->GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, SQT_E_NCCL, "ncclGetUniqueId: %s", na->GetErrorString(r));
+    memcpy(id_out, id.internal, SQT_COMM_ID_BYTES);
+    return SQT_OK;
+}
+
+extern "C" int sqt_comm_init(sqt_ctx *ctx, int rank, int world, const uint8_t id_in[SQT_COMM_ID_BYTES]) {
+    if (!ctx) return SQT_E_INVALID;
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SQT_E_INVALID, "bad rank/world %d/%d", rank, world);
+    if (world == 1) { ctx->rank = 0; ctx->world = 1; return SQT_OK; }
+    NcclApi *na = nccl_api();
+    if (!na->lib) return fail(ctx, SQT_E_NCCL, "%s", na->err.c_str());
+    CU(cudaSetDevice(ctx->device));
+    ncclUniqueId id; memcpy(id.internal, id_in, SQT_COMM_ID_BYTES);
+    ncclResult_t r = na->CommInitRank(&ctx->comm, world, id, rank);
+    if (r != 0) return fail(ctx, SQT_E_NCCL, "ncclCommInitRank: %s", na->GetErrorString(r));
+    ctx->rank = rank; ctx->world = world;
+    return SQT_OK;
+}
+
+extern "C" int sqt_comm_init_all(sqt_ctx **ctxs, int n) {
+    if (!ctxs || n < 1) return SQT_E_INVALID;
+    if (n == 1) { ctxs[0]->rank = 0; ctxs[0]->world = 1; return SQT_OK; }
+    NcclApi *na = nccl_api();
+    if (!na->lib) return fail(ctxs[0], SQT_E_NCCL, "%s", na->err.c_str());
+    std::vector<int> devs(n); std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+    ncclResult_t r = na->CommInitAll(comms.data(), n, devs.data());
+    if (r != 0) return fail(ctxs[0], SQT_E_NCCL, "ncclCommInitAll: %s", na->GetErrorString(r));
+    for (int i = 0; i < n; ++i) { ctxs[i]->comm = comms[i]; ctxs[i]->rank = i; ctxs[i]->world = n; }
+    return SQT_OK;
+}
+
+extern "C" int sqt_render_group(sqt_ctx **ctxs, int n, const sqt_camera *cam, const sqt_render_params *p,
+                                uint8_t *rgb8_out, float *accum_out, sqt_stats *stats) {
+    if (!ctxs || n < 1) return SQT_E_INVALID;
+    if (n == 1) return sqt_render(ctxs[0], cam, p, rgb8_out, accum_out, stats);
+    // one host thread per device: the ncclReduce calls of a single-process group must be issued concurrently
+    std::vector<int> rcs(n, 0);
+    std::vector<std::thread> th;
+    for (int i = 1; i < n; ++i)
+        th.emplace_back([&, i]() { rcs[i] = sqt_render(ctxs[i], cam, p, nullptr, nullptr, nullptr); });
+    rcs[0] = sqt_render(ctxs[0], cam, p, rgb8_out, accum_out, stats);
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n; ++i) if (rcs[i]) { if (i) ctxs[0]->err = ctxs[i]->err; return rcs[i]; }
+    return SQT_OK;
+}
+
+// ------------------------------------------------------------------------------ roofline microbenchmarks
+extern "C" int sqt_measure_fp32_peak(sqt_ctx *ctx, double *gops) {
+    if (!ctx || !gops) return SQT_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    float *d = nullptr; CU(cudaMalloc(&d, 16));
+    const int iters = 4096, grid = ctx->sm_count * 8, block = 256;
+    cudaStream_t st = ctx->stream;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(ctx->ev[0], st));
+        k_fp32_peak<<<grid, block, 0, st>>>(d, iters, 1.0000001f, 1e-7f);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[1], st));
+        CU(cudaStreamSynchronize(st));
+        const double ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+        const double ops = (double)grid * block * iters * 32.0;
+        if (rep > 0 && ops / ms * 1e-6 > best) best = ops / ms * 1e-6;
+    }
+    cudaFree(d);
+    *gops = best;
+    return SQT_OK;
+}
+
+extern "C" int sqt_measure_l2_bandwidth(sqt_ctx *ctx, double *gbs) {
+    if (!ctx || !gbs) return SQT_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const long long bytes = 32ll << 20, n4 = bytes / 16;
+    float4 *buf = nullptr; float *out = nullptr;
+    CU(cudaMalloc(&buf, bytes)); CU(cudaMalloc(&out, 16));
+    CU(cudaMemset(buf, 0, bytes));
+    cudaStream_t st = ctx->stream;
+    const int grid = ctx->sm_count * 8, block = 256, reps = 16;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(ctx->ev[0], st));
+        k_l2_read<<<grid, block, 0, st>>>(buf, n4, reps, out);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[1], st));
+        CU(cudaStreamSynchronize(st));
+        const double ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+        const double gb = (double)bytes * reps / ms * 1e-6;
+        if (rep > 0 && gb > best) best = gb;
+    }
+    cudaFree(buf); cudaFree(out);
+    *gbs = best;
+    return SQT_OK;
+}

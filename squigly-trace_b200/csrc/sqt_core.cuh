@@ -1,0 +1,456 @@
+// sqt_core.cuh -- per-ray / per-path device logic of the squigly-trace B200 backend.
+//
+// Everything here is SQT_HD (__host__ __device__) so that tests/ can compile the same logic with
+// g++ and check it against the oracle on the CPU box (tests/emu); the product only ever runs the
+// __device__ instantiation from sqt_kernels.cu.
+//
+// Exactness rules (hard part 2): every FP32 operation on the intersection and shading
+// path is an explicit round-to-nearest add/sub/mul/div/sqrt (X* wrappers = __f*_rn on the device,
+// never contracted into FMA); min/max follow the Haskell class defaults whenever a NaN could be
+// involved; comparisons are written exactly as in the reference.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SQT_HD __host__ __device__ __forceinline__
+#define SQT_HD_NOINLINE __host__ __device__
+#else
+#define SQT_HD inline
+#define SQT_HD_NOINLINE
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define XADD(a, b) __fadd_rn((a), (b))
+#define XSUB(a, b) __fsub_rn((a), (b))
+#define XMUL(a, b) __fmul_rn((a), (b))
+#define XDIV(a, b) __fdiv_rn((a), (b))
+#define XRCP(a) __frcp_rn((a))
+#define XSQRT(a) __fsqrt_rn((a))
+#define SQT_FMIN(a, b) fminf((a), (b))
+#define SQT_FMAX(a, b) fmaxf((a), (b))
+#define SQT_LDG4(p) __ldg((const float4 *)(p))
+#else
+// host build (tests/emu): compiled with -ffp-contract=off -fno-fast-math
+#define XADD(a, b) ((float)((float)(a) + (float)(b)))
+#define XSUB(a, b) ((float)((float)(a) - (float)(b)))
+#define XMUL(a, b) ((float)((float)(a) * (float)(b)))
+#define XDIV(a, b) ((float)((float)(a) / (float)(b)))
+#define XRCP(a) ((float)(1.0f / (float)(a)))
+#define XSQRT(a) sqrtf((a))
+#define SQT_FMIN(a, b) fminf((a), (b))
+#define SQT_FMAX(a, b) fmaxf((a), (b))
+#define SQT_LDG4(p) (*(const float4 *)(p))
+#if !defined(__CUDACC__)
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) int2 { int x, y; };
+#endif
+#endif
+
+namespace sqt {
+
+// ---------------------------------------------------------------------------- device records
+// Branch node, 48 B = 3 x 128-bit loads.  The box is the node's own clipped box, i.e. the `bbox`
+// argument intersectBIH' receives for this node (BIH.hs:111,130-141) -- a static property of the
+// tree, derived at upload time by copying planes (no arithmetic).
+//   q0 = (lo.x, lo.y, lo.z, hi.x)   q1 = (hi.y, hi.z, lmax, rmin)
+//   q2 = (left, right, lmeta, rmeta) as u32 bits:
+//        child is Branch: ref = index into the branch array, meta = 0
+//        child is Leaf  : ref = first triangle,             meta = LEAF | count
+//        lmeta additionally carries the split axis in bits 28..29
+constexpr uint32_t kLeaf = 0x80000000u;
+constexpr uint32_t kAxisShift = 28;
+constexpr uint32_t kCountMask = 0x0fffffffu;
+constexpr uint32_t kPhaseB = 0x80000000u;
+constexpr int kStackWords = 3 * 48 + 4;        // worst case: every frame parked in phase B (3 words)
+
+struct SceneView {
+    const float4 *nodes;     // 3 float4 per branch
+    const float4 *tris;      // 3 float4 per triangle: (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z, mat, orig, pad)
+    const float4 *mats;      // 3 float4 per material: (refl, surf.rgb) (emissive, emit.rgb) (ec.rgb, flags)
+    float root_lo[3], root_hi[3];
+    uint32_t n_branches, n_tris, n_mats;
+    uint32_t root_is_leaf;   // tree = Leaf: no box test at all (BIH.hs:105)
+};
+
+struct Ray { float ox, oy, oz, dx, dy, dz; };
+struct Hit { int tri; float t; float dist; };      // tri = index in leaf order, -1 = Nothing
+struct Counters { unsigned long long branch_visits, child_box_tests, tri_tests, rays; };
+
+SQT_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; __builtin_memcpy(&u, &f, 4); return u;
+#endif
+}
+SQT_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; __builtin_memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// Haskell Ord Float class defaults: max x y = if x <= y then y else x ; min x y = if x <= y then x else y
+SQT_HD float hs_max(float x, float y) { return (x <= y) ? y : x; }
+SQT_HD float hs_min(float x, float y) { return (x <= y) ? x : y; }
+// compare a b == GT  (anything against NaN is GT)
+SQT_HD bool cmp_gt(float a, float b) { return !(a < b) && !(a == b); }
+SQT_HD float sel3(int ax, float x, float y, float z) { return ax == 0 ? x : (ax == 1 ? y : z); }
+SQT_HD bool finite_f(float x) { return fabsf(x) < INFINITY; }   // false for inf and NaN
+
+// V3.hs:25-26  dot = (a*d)+(b*e)+(c*f)
+SQT_HD float dot3(float a, float b, float c, float d, float e, float f) {
+    return XADD(XADD(XMUL(a, d), XMUL(b, e)), XMUL(c, f));
+}
+
+// ------------------------------------------------------------------------------- slab tests
+// Geometry.hs:166-177, literal (used for the root box and for rays where a NaN can appear)
+SQT_HD bool slab_exact(float lx, float ly, float lz, float hx, float hy, float hz, const Ray &r,
+                       float dfx, float dfy, float dfz) {
+    float t1 = XMUL(XSUB(lx, r.ox), dfx), t2 = XMUL(XSUB(hx, r.ox), dfx);
+    float t3 = XMUL(XSUB(ly, r.oy), dfy), t4 = XMUL(XSUB(hy, r.oy), dfy);
+    float t5 = XMUL(XSUB(lz, r.oz), dfz), t6 = XMUL(XSUB(hz, r.oz), dfz);
+    float tmin = hs_max(hs_max(hs_min(t1, t2), hs_min(t3, t4)), hs_min(t5, t6));
+    float tmax = hs_min(hs_min(hs_max(t1, t2), hs_max(t3, t4)), hs_max(t5, t6));
+    return tmax > 0.0f && tmin < tmax;
+}
+
+// Both child boxes of a branch (BIH.hs:128-141).  `safe` rays (all 1/dir finite, origin not NaN)
+// cannot produce a NaN slab value, and without NaNs min/max are exact, order-free operations whose
+// zero sign never reaches the two comparisons -- so the hardware FMNMX path is used and the planes
+// shared by both children are evaluated once.  Unsafe rays take the literal path.
+SQT_HD void slab_children(const float4 &q0, const float4 &q1, int ax, const Ray &r, float dfx, float dfy,
+                          float dfz, bool safe, bool &hit_l, bool &hit_r) {
+    const float lmax = q1.z, rmin = q1.w;
+    if (safe) {
+        float t1 = XMUL(XSUB(q0.x, r.ox), dfx), t2 = XMUL(XSUB(q0.w, r.ox), dfx);
+        float t3 = XMUL(XSUB(q0.y, r.oy), dfy), t4 = XMUL(XSUB(q1.x, r.oy), dfy);
+        float t5 = XMUL(XSUB(q0.z, r.oz), dfz), t6 = XMUL(XSUB(q1.y, r.oz), dfz);
+        float mnx = SQT_FMIN(t1, t2), mxx = SQT_FMAX(t1, t2);
+        float mny = SQT_FMIN(t3, t4), mxy = SQT_FMAX(t3, t4);
+        float mnz = SQT_FMIN(t5, t6), mxz = SQT_FMAX(t5, t6);
+        float o_ax = sel3(ax, r.ox, r.oy, r.oz), df_ax = sel3(ax, dfx, dfy, dfz);
+        float tlo = sel3(ax, t1, t3, t5), thi = sel3(ax, t2, t4, t6);
+        float tlm = XMUL(XSUB(lmax, o_ax), df_ax), trm = XMUL(XSUB(rmin, o_ax), df_ax);
+        // the two axes that are not split
+        float mn_o = sel3(ax, SQT_FMAX(mny, mnz), SQT_FMAX(mnx, mnz), SQT_FMAX(mnx, mny));
+        float mx_o = sel3(ax, SQT_FMIN(mxy, mxz), SQT_FMIN(mxx, mxz), SQT_FMIN(mxx, mxy));
+        float tmin_l = SQT_FMAX(mn_o, SQT_FMIN(tlo, tlm)), tmax_l = SQT_FMIN(mx_o, SQT_FMAX(tlo, tlm));
+        float tmin_r = SQT_FMAX(mn_o, SQT_FMIN(trm, thi)), tmax_r = SQT_FMIN(mx_o, SQT_FMAX(trm, thi));
+        hit_l = tmax_l > 0.0f && tmin_l < tmax_l;
+        hit_r = tmax_r > 0.0f && tmin_r < tmax_r;
+    } else {
+        float lx = q0.x, ly = q0.y, lz = q0.z, hx = q0.w, hy = q1.x, hz = q1.y;
+        hit_l = slab_exact(lx, ly, lz, ax == 0 ? lmax : hx, ax == 1 ? lmax : hy, ax == 2 ? lmax : hz, r, dfx, dfy, dfz);
+        hit_r = slab_exact(ax == 0 ? rmin : lx, ax == 1 ? rmin : ly, ax == 2 ? rmin : lz, hx, hy, hz, r, dfx, dfy, dfz);
+    }
+}
+
+// ------------------------------------------------------------------------- Moller-Trumbore
+// Geometry.hs:117-142 with edge1/edge2 precomputed.  Guard order a -> u -> v -> t.
+SQT_HD bool moller_trumbore(const float4 &a0, const float4 &a1, const float4 &a2, const Ray &r, float &t_out,
+                            float &dist_out) {
+    const float eps = 0.0001f;
+    const float v0x = a0.x, v0y = a0.y, v0z = a0.z;
+    const float e1x = a0.w, e1y = a1.x, e1z = a1.y;
+    const float e2x = a1.z, e2y = a1.w, e2z = a2.x;
+    // h = rayDir `cross` edge2
+    float hx = XSUB(XMUL(r.dy, e2z), XMUL(r.dz, e2y));
+    float hy = XSUB(XMUL(r.dz, e2x), XMUL(r.dx, e2z));
+    float hz = XSUB(XMUL(r.dx, e2y), XMUL(r.dy, e2x));
+    float a = dot3(e1x, e1y, e1z, hx, hy, hz);
+    if (a > -eps && a < eps) return false;
+    float f = XRCP(a);
+    float sx = XSUB(r.ox, v0x), sy = XSUB(r.oy, v0y), sz = XSUB(r.oz, v0z);
+    float u = XMUL(f, dot3(sx, sy, sz, hx, hy, hz));
+    if (u < 0.0f || u > 1.0f) return false;
+    // q = s `cross` edge1
+    float qx = XSUB(XMUL(sy, e1z), XMUL(sz, e1y));
+    float qy = XSUB(XMUL(sz, e1x), XMUL(sx, e1z));
+    float qz = XSUB(XMUL(sx, e1y), XMUL(sy, e1x));
+    float v = XMUL(f, dot3(r.dx, r.dy, r.dz, qx, qy, qz));
+    if (v < 0.0f || XADD(u, v) > 1.0f) return false;
+    float t = XMUL(f, dot3(e2x, e2y, e2z, qx, qy, qz));
+    if (!(t > eps)) return false;
+    // outInter = rayVert + t *^ rayDir ; rayDist = norm (outInter - rayVert)
+    float px = XADD(r.ox, XMUL(t, r.dx)), py = XADD(r.oy, XMUL(t, r.dy)), pz = XADD(r.oz, XMUL(t, r.dz));
+    float ex = XSUB(px, r.ox), ey = XSUB(py, r.oy), ez = XSUB(pz, r.oz);
+    t_out = t;
+    dist_out = XSQRT(dot3(ex, ey, ez, ex, ey, ez));
+    return true;
+}
+
+// Leaf (BIH.hs:105-109): V.mapMaybe over the leaf's triangles, minimumBy (comparing dist).
+// base-4.9 minimumBy = foldr1 min' with min' x y = GT -> y ; _ -> x : walk from the last triangle
+// to the first, the earlier one wins unless it is strictly farther.
+template <bool COUNT>
+SQT_HD Hit leaf_test(const SceneView &sc, const Ray &r, uint32_t first, uint32_t count, Counters *cn) {
+    Hit best; best.tri = -1; best.t = 0.0f; best.dist = 0.0f;
+    if (COUNT) cn->tri_tests += count;
+    for (int i = (int)count - 1; i >= 0; --i) {
+        const float4 *p = sc.tris + 3 * (size_t)(first + (uint32_t)i);
+        float4 a0 = SQT_LDG4(p), a1 = SQT_LDG4(p + 1), a2 = SQT_LDG4(p + 2);
+        float t, dist;
+        if (moller_trumbore(a0, a1, a2, r, t, dist)) {
+            if (best.tri < 0 || !cmp_gt(dist, best.dist)) { best.tri = (int)(first + (uint32_t)i); best.t = t; best.dist = dist; }
+        }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------ traversal
+// intersectBIH (BIH.hs:101-141) as an explicit-stack state machine that visits exactly the
+// subtrees the recursion visits, in the same order, and combines results with the same rules:
+//   * the own-box test of BIH.hs:112 is evaluated for the root only -- for every other branch it
+//     repeats, with identical operands, the test its parent just passed at BIH.hs:128-129;
+//   * a branch whose two children are both hit pushes one word (its index, "phase A") and enters
+//     the near child; when that subtree returns, isClose (BIH.hs:121-123) is evaluated on the near
+//     subtree's OWN result; if the far child must still be visited and near had a hit, that hit is
+//     parked on the stack ("phase B", 3 words) and merged with min' when the far subtree returns.
+template <bool COUNT>
+SQT_HD Hit traverse(const SceneView &sc, const Ray &r, Counters *cn) {
+    Hit cur; cur.tri = -1; cur.t = 0.0f; cur.dist = 0.0f;
+    if (COUNT) cn->rays += 1;
+    if (sc.root_is_leaf) return leaf_test<COUNT>(sc, r, 0u, sc.n_tris, cn);
+    const float dfx = XRCP(r.dx), dfy = XRCP(r.dy), dfz = XRCP(r.dz);
+    const bool safe = finite_f(dfx) && finite_f(dfy) && finite_f(dfz) && finite_f(r.dx) && finite_f(r.dy) &&
+                      finite_f(r.dz) && finite_f(r.ox) && finite_f(r.oy) && finite_f(r.oz);
+    if (!slab_exact(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], r, dfx,
+                    dfy, dfz))
+        return cur;
+    uint32_t stack[kStackWords];
+    int sp = 0;
+    uint32_t child = 0u, meta = 0u;
+    for (;;) {
+        bool have = true;
+        // ---- descend: branch visits until a leaf is reached or both children are missed
+        while (!(meta & kLeaf)) {
+            const float4 *np = sc.nodes + 3 * (size_t)child;
+            const float4 q0 = SQT_LDG4(np), q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
+            const uint32_t left = f2u(q2.x), right = f2u(q2.y), lmeta = f2u(q2.z), rmeta = f2u(q2.w);
+            const int ax = (int)((lmeta >> kAxisShift) & 3u);
+            bool hit_l, hit_r;
+            slab_children(q0, q1, ax, r, dfx, dfy, dfz, safe, hit_l, hit_r);
+            if (COUNT) { cn->branch_visits += 1; cn->child_box_tests += 2; }
+            const bool ltr = sel3(ax, r.dx, r.dy, r.dz) > 0.0f;          // BIH.hs:127
+            if (hit_l && hit_r) {
+                stack[sp++] = child;                                      // phase A frame
+                if (ltr) { child = left; meta = lmeta & ~(3u << kAxisShift); }
+                else { child = right; meta = rmeta; }
+            } else if (hit_l) { child = left; meta = lmeta & ~(3u << kAxisShift); }
+            else if (hit_r) { child = right; meta = rmeta; }
+            else { have = false; break; }
+        }
+        if (have) cur = leaf_test<COUNT>(sc, r, child, meta & kCountMask, cn);
+        else { cur.tri = -1; }
+        // ---- unwind
+        bool resume = false;
+        while (sp > 0) {
+            const uint32_t top = stack[sp - 1];
+            if (top & kPhaseB) {                                          // far subtree returned: min' near far
+                Hit rn; rn.tri = (int)(top & ~kPhaseB); rn.dist = u2f(stack[sp - 2]); rn.t = u2f(stack[sp - 3]);
+                sp -= 3;
+                if (cur.tri < 0 || !cmp_gt(rn.dist, cur.dist)) cur = rn;
+                continue;
+            }
+            sp -= 1;                                                      // near subtree of branch `top` returned
+            const float4 *np = sc.nodes + 3 * (size_t)top;
+            const float4 q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
+            const uint32_t lmeta = f2u(q2.z);
+            const int ax = (int)((lmeta >> kAxisShift) & 3u);
+            const float d_ax = sel3(ax, r.dx, r.dy, r.dz);
+            const bool ltr = d_ax > 0.0f;
+            if (cur.tri >= 0) {
+                const float p = XADD(sel3(ax, r.ox, r.oy, r.oz), XMUL(cur.t, d_ax));   // intersectPoint on ax
+                const bool close = ltr ? (p < q1.w) : (p > q1.z);         // BIH.hs:121-123
+                if (close) continue;
+                stack[sp] = f2u(cur.t); stack[sp + 1] = f2u(cur.dist); stack[sp + 2] = (uint32_t)cur.tri | kPhaseB;
+                sp += 3;
+            }
+            if (ltr) { child = f2u(q2.y); meta = f2u(q2.w); }
+            else { child = f2u(q2.x); meta = lmeta & ~(3u << kAxisShift); }
+            resume = true;
+            break;
+        }
+        if (!resume) return cur;
+    }
+}
+
+// ------------------------------------------------------------------------------------- RNG
+// Philox4x32-10; stream = the integer the reference hands to mkTFGen (Lib.hs:85-86), j = index of
+// the Word32 in that generator's output.  counter = (stream lo, stream hi, j/4, "SQTR"), key = seed.
+SQT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+#if defined(__CUDA_ARCH__)
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Lib.hs:183-188 at (0,1): Word32 -> Float (round to nearest) / 2^32 ; inclusive of 1.0
+SQT_HD float random_r01(uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    return XMUL(__uint2float_rn(n), 2.3283064365386963e-10f);
+#else
+    return XMUL((float)n, 2.3283064365386963e-10f);
+#endif
+}
+
+struct DrawCache {          // the four draws of one Philox block of the current sample
+    uint32_t w[4];
+    int block;              // -1 = empty
+};
+SQT_HD float draw(DrawCache &dc, uint64_t seed, uint64_t stream, uint32_t j) {
+    const int b = (int)(j >> 2);
+    if (b != dc.block) {
+        philox4x32_10((uint32_t)stream, (uint32_t)(stream >> 32), (uint32_t)b, 0x52545153u, (uint32_t)seed,
+                      (uint32_t)(seed >> 32), dc.w);
+        dc.block = b;
+    }
+    const uint32_t k = j & 3u;
+    const uint32_t w = k == 0 ? dc.w[0] : (k == 1 ? dc.w[1] : (k == 2 ? dc.w[2] : dc.w[3]));
+    return random_r01(w);
+}
+
+// ------------------------------------------------------------------------------------ trig
+// "sqt trig" (DESIGN.md section 6): plain binary32 polynomials, fixed operation order, no FMA, so the
+// device and the oracle's restatement agree bit for bit.  Arguments: x in [0, 2*pi].
+SQT_HD void sqt_sincos(float x, float &s_out, float &c_out) {
+    const int k = (int)XADD(XMUL(x, 0.63661975f), 0.5f);
+    const float kf = (float)k;
+    const float r = XSUB(XSUB(XSUB(x, XMUL(kf, 1.5703125f)), XMUL(kf, 4.837512969970703125e-4f)),
+                         XMUL(kf, 7.54978995489188216e-8f));
+    const float z = XMUL(r, r);
+    float s = XADD(XMUL(-1.9515295891e-4f, z), 8.3321608736e-3f);
+    s = XSUB(XMUL(s, z), 1.6666654611e-1f);
+    s = XADD(XMUL(XMUL(s, z), r), r);
+    float c = XSUB(XMUL(2.443315711809948e-5f, z), 1.388731625493765e-3f);
+    c = XADD(XMUL(c, z), 4.166664568298827e-2f);
+    c = XMUL(XMUL(c, z), z);
+    c = XSUB(c, XMUL(0.5f, z));
+    c = XADD(c, 1.0f);
+    const int q = k & 3;
+    s_out = q == 0 ? s : (q == 1 ? c : (q == 2 ? -s : -c));
+    c_out = q == 0 ? c : (q == 1 ? -s : (q == 2 ? -c : s));
+}
+SQT_HD float sqt_asin_core(float x, float z) {
+    float p = XADD(XMUL(4.2163199048e-2f, z), 2.4181311049e-2f);
+    p = XADD(XMUL(p, z), 4.5470025998e-2f);
+    p = XADD(XMUL(p, z), 7.4953002686e-2f);
+    p = XADD(XMUL(p, z), 1.6666752422e-1f);
+    return XADD(XMUL(XMUL(p, z), x), x);
+}
+SQT_HD float sqt_acos(float x) {
+    if (x < -0.5f) {
+        const float z = XMUL(0.5f, XADD(1.0f, x)), y = XSQRT(z);
+        return XSUB(3.14159265358979323846f, XMUL(2.0f, sqt_asin_core(y, z)));
+    }
+    if (x > 0.5f) {
+        const float z = XMUL(0.5f, XSUB(1.0f, x)), y = XSQRT(z);
+        return XMUL(2.0f, sqt_asin_core(y, z));
+    }
+    return XSUB(1.57079632679489661923f, sqt_asin_core(x, XMUL(x, x)));
+}
+SQT_HD float sqt_atan(float x) {   // x >= 0
+    float y;
+    if (x > 2.414213562373095f) { y = 1.57079632679489661923f; x = -XDIV(1.0f, x); }
+    else if (x > 0.4142135623730950f) { y = 0.78539816339744830962f; x = XDIV(XSUB(x, 1.0f), XADD(x, 1.0f)); }
+    else y = 0.0f;
+    const float z = XMUL(x, x);
+    float p = XSUB(XMUL(8.05374449538e-2f, z), 1.38776856032e-1f);
+    p = XADD(XMUL(p, z), 1.99777106478e-1f);
+    p = XSUB(XMUL(p, z), 3.33329491539e-1f);
+    return XADD(y, XADD(XMUL(XMUL(p, z), x), x));
+}
+
+// -------------------------------------------------------------------------------- shading
+struct RenderParams {
+    int rows, cols, xdiv, ydiv, seed_stride, spp, max_depth, mode;
+    unsigned long long seed;
+    int rank, world, split_samples, primary_reuse;
+    float cam_pos[3], cam_rot[9];
+    int terminate_on_black;     // host proved C*L stays finite: a surface with surfColor == 0 ends the path exactly
+};
+
+// makeRay (Lib.hs:107-114) + rotVert (Geometry.hs:104-107: row vector x matrix, sum = foldl (+) 0)
+SQT_HD Ray make_ray(const RenderParams &p, int y, int x) {
+    const float ww = (float)p.xdiv, hh = (float)p.ydiv;
+    const float xo = XDIV(XSUB((float)x, XDIV(ww, 2.0f)), ww);
+    const float yo = XDIV(XSUB(XDIV(hh, 2.0f), (float)y), hh);
+    const float *R = p.cam_rot;
+    Ray r;
+    r.ox = p.cam_pos[0]; r.oy = p.cam_pos[1]; r.oz = p.cam_pos[2];
+    r.dx = XADD(XADD(XADD(0.0f, XMUL(1.0f, R[0])), XMUL(xo, R[3])), XMUL(yo, R[6]));
+    r.dy = XADD(XADD(XADD(0.0f, XMUL(1.0f, R[1])), XMUL(xo, R[4])), XMUL(yo, R[7]));
+    r.dz = XADD(XADD(XADD(0.0f, XMUL(1.0f, R[2])), XMUL(xo, R[5])), XMUL(yo, R[8]));
+    return r;
+}
+
+SQT_HD float hs_signum(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : x); }
+
+// bounceRay (Lib.hs:155-160) at a hit on triangle `tri` (leaf order) with hit parameter t:
+// x = draw j decides scatter/reflect; scatter reuses x as the azimuth draw and takes draw j+1 as the
+// polar draw.  Returns the new ray; origin = intersectPoint = o + t*^d.
+SQT_HD Ray bounce_ray(const SceneView &sc, const Ray &in, int tri, float t, float reflective, DrawCache &dc,
+                      unsigned long long seed, unsigned long long stream, uint32_t j) {
+    const float4 *p = sc.tris + 3 * (size_t)tri;
+    const float4 a0 = SQT_LDG4(p), a1 = SQT_LDG4(p + 1), a2 = SQT_LDG4(p + 2);
+    const float e1x = a0.w, e1y = a1.x, e1z = a1.y, e2x = a1.z, e2y = a1.w, e2z = a2.x;
+    // normal = (b - a) `cross` (c - a)   Geometry.hs:79-80
+    const float nx = XSUB(XMUL(e1y, e2z), XMUL(e1z, e2y));
+    const float ny = XSUB(XMUL(e1z, e2x), XMUL(e1x, e2z));
+    const float nz = XSUB(XMUL(e1x, e2y), XMUL(e1y, e2x));
+    Ray out;
+    out.ox = XADD(in.ox, XMUL(t, in.dx)); out.oy = XADD(in.oy, XMUL(t, in.dy)); out.oz = XADD(in.oz, XMUL(t, in.dz));
+    const float x = draw(dc, seed, stream, j);
+    if (reflective < x) {                       // scatterRay, Lib.hs:166-172 ; randomVector Lib.hs:192-198
+        const float v = draw(dc, seed, stream, j + 1u);
+        const float th = XMUL(6.28318530717958647692f, x);             // 2 * pi * u
+        const float ph = sqt_acos(XSUB(XMUL(2.0f, v), 1.0f));
+        float sth, cth, sph, cph;
+        sqt_sincos(th, sth, cth);
+        sqt_sincos(ph, sph, cph);
+        const float ndx = XMUL(cth, sph), ndy = XMUL(sth, sph), ndz = cph;
+        const float so = hs_signum(dot3(in.dx, in.dy, in.dz, nx, ny, nz));
+        const float sn = hs_signum(dot3(ndx, ndy, ndz, nx, ny, nz));
+        const bool flip = (so == sn);
+        out.dx = flip ? -ndx : ndx; out.dy = flip ? -ndy : ndy; out.dz = flip ? -ndz : ndz;
+    } else {                                    // reflectRay, Lib.hs:176-181
+        const float nn = XSQRT(dot3(nx, ny, nz, nx, ny, nz));
+        const float ux = XDIV(nx, nn), uy = XDIV(ny, nn), uz = XDIV(nz, nn);
+        const float k = XMUL(2.0f, dot3(ux, uy, uz, in.dx, in.dy, in.dz));
+        out.dx = XSUB(in.dx, XMUL(k, ux)); out.dy = XSUB(in.dy, XMUL(k, uy)); out.dz = XSUB(in.dz, XMUL(k, uz));
+    }
+    return out;
+}
+
+// rgbFloatToPixelRGB (Lib.hs:93-104); floor :: Float -> Word8 wraps through Integer, NaN -> 0
+SQT_HD uint8_t to_w8(float s255) {
+    if (s255 != s255) return 0;
+    const float f = floorf(s255);
+    long long w = (fabsf(f) < 9.0e18f) ? (long long)f : 0;
+    uint32_t b = (uint32_t)((unsigned long long)w & 0xffull);
+    return (uint8_t)(b < 255u ? b : 255u);
+}
+SQT_HD void tone_map(float r, float g, float b, uint8_t out[3]) {
+    const float maxc = hs_max(hs_max(r, g), b), minc = hs_min(hs_min(r, g), b);
+    const float lightness = XMUL(0.5f, XADD(maxc, minc));
+    const float intensity = XDIV(sqt_atan(lightness), 1.57079632679489661923f);
+    const float k = XDIV(intensity, maxc);
+    out[0] = to_w8(XMUL(XMUL(k, r), 255.0f));
+    out[1] = to_w8(XMUL(XMUL(k, g), 255.0f));
+    out[2] = to_w8(XMUL(XMUL(k, b), 255.0f));
+}
+
+}  // namespace sqt
