@@ -948,6 +948,31 @@ int orc_render(orc_scene *s, const float *cam12, const orc_params *p, float *acc
     return 0;
 }
 
+/* Lib.hs:79-89 for the pixels [pix_lo, pix_hi) of a frame only (same seeds and rays as in the full frame), so
+ * that tests can check rows of a full-size GPU render.  accum has (pix_hi - pix_lo) * 3 floats. */
+typedef struct { render_ctx rc; int64_t off; } window_ctx;
+static void window_chunk(void *ctx, int64_t lo, int64_t hi, int tid)
+{
+    window_ctx *w = (window_ctx *)ctx;
+    render_chunk(&w->rc, lo + w->off, hi + w->off, tid);
+}
+int orc_render_window(orc_scene *s, const float *cam12, const orc_params *p, int64_t pix_lo, int64_t pix_hi, float *accum,
+                      int nthreads)
+{
+    if (s->n_nodes == 0 || pix_lo < 0 || pix_hi > (int64_t)p->rows * p->cols || pix_lo > pix_hi) return 1;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 512) nthreads = 512;
+    window_ctx w;
+    w.rc.s = s; w.rc.cam = cam12; w.rc.p = *p; w.rc.rgb8 = NULL;
+    w.rc.accum = accum - 3 * pix_lo;          /* render_chunk indexes by absolute pixel */
+    w.rc.cn = (orc_counters *)calloc((size_t)nthreads, sizeof(orc_counters));
+    w.rc.samples = (uint64_t *)calloc((size_t)nthreads, sizeof(uint64_t));
+    w.off = pix_lo;
+    parallel_for(pix_hi - pix_lo, 64, nthreads, window_chunk, &w);
+    free(w.rc.cn); free(w.rc.samples);
+    return 0;
+}
+
 /* helpers exported for unit tests */
 float orc_random_r01(uint32_t n) { return random_r01(n); }
 uint32_t orc_draw_word(uint64_t seed, uint64_t stream, uint32_t j) { return draw_word(seed, stream, j); }

@@ -47,6 +47,8 @@ def lib():
         L.orc_make_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_render.restype = C.c_int
         L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_render_window.restype = C.c_int
+        L.orc_render_window.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
         L.orc_tone_map.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         L.orc_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_random_r01.restype = C.c_float
@@ -172,6 +174,16 @@ class Scene:
         return dict(accum=accum, rgb8=rgb8, rays=int(stats[0]), samples=int(stats[1]),
                     counters=dict(branch_visits=int(cn[0]), child_box_tests=int(cn[1]), own_box_tests=int(cn[2]),
                                   tri_tests=int(cn[3]), rays=int(cn[4])))
+
+
+def render_window(scene, cam12, params, pix_lo, pix_hi, nthreads=None):
+    """Radiance sums of pixels [pix_lo, pix_hi) of the frame described by params (row-major pixel index)."""
+    cam12 = np.ascontiguousarray(cam12, np.float32)
+    acc = np.zeros((pix_hi - pix_lo, 3), np.float32)
+    rc = lib().orc_render_window(scene.h, _p(cam12), C.byref(params), pix_lo, pix_hi, _p(acc), nthreads or os.cpu_count())
+    if rc:
+        raise RuntimeError("orc_render_window failed")
+    return acc
 
 
 def load_camera(path):

@@ -53,49 +53,70 @@ __device__ __forceinline__ void flush_stats(DeviceStats *ds, const PathStats &st
     }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(256) k_intersect_batch(SceneView sc, const float *__restrict__ org,
-                                                         const float *__restrict__ dir, long long n,
-                                                         int *__restrict__ tri_out, float *__restrict__ dist_out,
-                                                         float *__restrict__ point_out, DeviceStats *ds) {
-    Counters cn = {0, 0, 0, 0};
-    PathStats st = {0, 0, 0};
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Ray r;
-        r.ox = org[3 * i]; r.oy = org[3 * i + 1]; r.oz = org[3 * i + 2];
-        r.dx = dir[3 * i]; r.dy = dir[3 * i + 1]; r.dz = dir[3 * i + 2];
-        const Hit h = traverse<COUNT>(sc, r, &cn);
-        st.rays += 1;
-        int orig = -1;
-        if (h.tri >= 0) orig = (int)f2u(SQT_LDG4(sc.tris + 3 * (size_t)h.tri + 2).z);
-        tri_out[i] = orig;
-        if (dist_out) dist_out[i] = h.tri >= 0 ? h.dist : 0.0f;
-        if (point_out) {
-            const bool hit = h.tri >= 0;
-            point_out[3 * i] = hit ? XADD(r.ox, XMUL(h.t, r.dx)) : 0.0f;
-            point_out[3 * i + 1] = hit ? XADD(r.oy, XMUL(h.t, r.dy)) : 0.0f;
-            point_out[3 * i + 2] = hit ? XADD(r.oz, XMUL(h.t, r.dz)) : 0.0f;
+// Scheduling knobs of the warp-synchronous loop (runtime so that they can be tuned without rebuilding):
+//   a_leave : leave the traversal phase once at most this many lanes still want a traversal step
+//   b_leave : leave the triangle phase once fewer than this many lanes still have triangles to test
+//   c_min   : run the regeneration phase only when at least this many lanes are done (or nothing else can run)
+struct Tune { int a_leave, b_leave, c_min; };
+
+// The persistent warp loop.  Every lane of the warp stays in it until all 32 have run out of work; the phase
+// boundaries are warp votes, so divergent lanes are forced back together three times per round instead of
+// drifting apart through the data-dependent traversal (which is what an ordinary per-lane loop nest compiles to).
+template <bool COUNT, class Policy>
+__device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Counters *cn, const Tune tn) {
+    const unsigned FULL = 0xffffffffu;
+    uint32_t stack[kStackWords];
+    TravLane L;
+    L.stack = stack;
+    L.state = ST_DONE; L.sp = 0; L.i = 0; L.child = 0u; L.meta = 0u; L.safe = true;
+    L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
+    L.dfx = L.dfy = L.dfz = 0.0f;
+    L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
+    for (;;) {
+        // ---- regeneration: lanes whose ray finished consume the hit and produce their next ray
+        const unsigned m_done = __ballot_sync(FULL, L.state == ST_DONE);
+        const unsigned m_busy = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET || L.state == ST_LEAF);
+        if (m_done != 0u && (__popc(m_done) >= tn.c_min || m_busy == 0u)) {
+            if (L.state == ST_DONE) pol.template regen<COUNT>(sc, L, cn);
+            __syncwarp(FULL);
+        } else if (m_busy == 0u) break;                       // every lane is ST_EXIT
+        // ---- traversal steps (branch visits, stack pops)
+        unsigned m = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET);
+        while (m != 0u) {
+            if (L.state == ST_RET) ret_step(sc, L);
+            if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
+            m = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET);
+            if (__popc(m) <= tn.a_leave) break;
+        }
+        // ---- triangle steps (one Moller-Trumbore test per lane per iteration)
+        m = __ballot_sync(FULL, L.state == ST_LEAF);
+        while (m != 0u) {
+            if (L.state == ST_LEAF) tri_step(sc, L);
+            m = __ballot_sync(FULL, L.state == ST_LEAF);
+            if (__popc(m) < tn.b_leave) break;
         }
     }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_intersect_batch(SceneView sc, const float *__restrict__ org,
+                                                         const float *__restrict__ dir, long long n,
+                                                         int *__restrict__ tri_out, float *__restrict__ dist_out,
+                                                         float *__restrict__ point_out, DeviceStats *ds, Tune tn) {
+    Counters cn = {0, 0, 0, 0};
+    PathStats st = {0, 0, 0};
+    BatchPolicy pol(org, dir, n, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, tri_out,
+                    dist_out, point_out, st);
+    warp_loop<COUNT>(sc, pol, &cn, tn);
     flush_stats(ds, st, cn, COUNT);
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(256) k_primary(SceneView sc, RenderParams p, int2 *__restrict__ prim, DeviceStats *ds) {
+__global__ void __launch_bounds__(128) k_primary(SceneView sc, RenderParams p, int2 *__restrict__ prim, DeviceStats *ds, Tune tn) {
     Counters cn = {0, 0, 0, 0};
     PathStats st = {0, 0, 0};
-    const long long nwork = work_items(p);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += stride) {
-        const long long pixel = work_to_pixel(p, w);
-        if (pixel < 0) continue;
-        const int y = (int)(pixel / p.cols), x = (int)(pixel % p.cols);
-        const Ray r = make_ray(p, y, x);
-        const Hit h = traverse<COUNT>(sc, r, &cn);
-        st.rays += 1;
-        prim[pixel] = make_int2(h.tri, (int)f2u(h.t));
-    }
+    PrimaryPolicy pol(p, prim, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, st);
+    warp_loop<COUNT>(sc, pol, &cn, tn);
     flush_stats(ds, st, cn, COUNT);
 }
 
@@ -115,25 +136,22 @@ struct DeviceFetch {
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, const int2 *__restrict__ prim,
-                                               float *__restrict__ accum, DeviceStats *ds) {
+                                               float *__restrict__ accum, DeviceStats *ds, Tune tn) {
     Counters cn = {0, 0, 0, 0};
     PathStats st = {0, 0, 0};
     DeviceFetch fetch = {&ds->work_next, work_items(p)};
-    render_lane<COUNT>(sc, p, prim, accum, fetch, &cn, st);
-    __syncwarp();
+    uint16_t pm[SQT_MAX_DEPTH];
+    PathPolicy<DeviceFetch> pol(p, prim, accum, fetch, st, pm);
+    warp_loop<COUNT>(sc, pol, &cn, tn);
     flush_stats(ds, st, cn, COUNT);
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(256) k_raycast(SceneView sc, RenderParams p, float *__restrict__ accum, DeviceStats *ds) {
+__global__ void __launch_bounds__(128) k_raycast(SceneView sc, RenderParams p, float *__restrict__ accum, DeviceStats *ds, Tune tn) {
     Counters cn = {0, 0, 0, 0};
     PathStats st = {0, 0, 0};
-    const long long nwork = work_items(p);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += stride) {
-        const long long pixel = work_to_pixel(p, w);
-        if (pixel >= 0) raycast_pixel<COUNT>(sc, p, pixel, accum, &cn, st);
-    }
+    CastPolicy pol(p, accum, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, st);
+    warp_loop<COUNT>(sc, pol, &cn, tn);
     flush_stats(ds, st, cn, COUNT);
 }
 
@@ -239,6 +257,7 @@ struct sqt_ctx {
     int *d_tri = nullptr;
     // pinned host staging for image I/O
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
+    Tune tune = {0, 1, 1};
     // group
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -281,6 +300,10 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
     for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
     CU(cudaMalloc(&c->d_stats, sizeof(DeviceStats)));
     CU(cudaMallocHost(&c->h_stats, sizeof(DeviceStats)));
+    if (const char *t = getenv("SQT_TUNE")) {        // "a_leave,b_leave,c_min" -- scheduling knobs only, results do not depend on them
+        int a, b, cm;
+        if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->tune = {a, b, cm};
+    }
     *out = c;
     return SQT_OK;
 }
@@ -375,6 +398,15 @@ static int ensure_rays(sqt_ctx *ctx, long long n) {
     ctx->cap_rays = n;
     return SQT_OK;
 }
+// persistent launch: as many 128-lane CTAs as stay resident on the 148 SMs (never more than the work needs)
+template <class K>
+static int persistent_grid(sqt_ctx *ctx, K kernel, long long nwork) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm, want = (nwork + 127) / 128;
+    if (want < grid) grid = want ? want : 1;
+    return (int)grid;
+}
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 // ------------------------------------------------------------------------------ intersect_batch
@@ -393,15 +425,14 @@ extern "C" int sqt_intersect_batch(sqt_ctx *ctx, const float *org, const float *
     CU(cudaMemcpyAsync(ctx->d_dir, dir, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), st));
     CU(cudaEventRecord(ctx->ev[1], st));
-    const int block = 256;
-    long long want = (n + block - 1) / block, cap = (long long)ctx->sm_count * 16;
-    const int grid = (int)(want < cap ? want : cap);
     if (stats)      // instrumented variant: fills the visit/test counters
-        k_intersect_batch<true><<<grid, block, 0, st>>>(ctx->sc, ctx->d_org, ctx->d_dir, n, ctx->d_tri, dist_out ? ctx->d_dist : nullptr,
-                                                        point_out ? ctx->d_point : nullptr, ctx->d_stats);
+        k_intersect_batch<true><<<persistent_grid(ctx, k_intersect_batch<true>, n), 128, 0, st>>>(
+            ctx->sc, ctx->d_org, ctx->d_dir, n, ctx->d_tri, dist_out ? ctx->d_dist : nullptr, point_out ? ctx->d_point : nullptr,
+            ctx->d_stats, ctx->tune);
     else
-        k_intersect_batch<false><<<grid, block, 0, st>>>(ctx->sc, ctx->d_org, ctx->d_dir, n, ctx->d_tri, dist_out ? ctx->d_dist : nullptr,
-                                                         point_out ? ctx->d_point : nullptr, ctx->d_stats);
+        k_intersect_batch<false><<<persistent_grid(ctx, k_intersect_batch<false>, n), 128, 0, st>>>(
+            ctx->sc, ctx->d_org, ctx->d_dir, n, ctx->d_tri, dist_out ? ctx->d_dist : nullptr, point_out ? ctx->d_point : nullptr,
+            ctx->d_stats, ctx->tune);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[2], st));
     CU(cudaMemcpyAsync(tri_out, ctx->d_tri, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -458,31 +489,21 @@ static int enqueue_render(sqt_ctx *ctx, const RenderParams &d, bool count, uint3
     const long long nwork = work_items(d);
     uint32_t nl = 0;
     if (d.mode == 1) {
-        const int block = 256; long long want = (nwork + block - 1) / block, cap = (long long)ctx->sm_count * 16;
-        const int grid = (int)(want < cap ? (want ? want : 1) : cap);
         CU(cudaEventRecord(ctx->ev[1], st));
-        if (count) k_raycast<true><<<grid, block, 0, st>>>(ctx->sc, d, ctx->d_accum, ctx->d_stats);
-        else k_raycast<false><<<grid, block, 0, st>>>(ctx->sc, d, ctx->d_accum, ctx->d_stats);
+        if (count) k_raycast<true><<<persistent_grid(ctx, k_raycast<true>, nwork), 128, 0, st>>>(ctx->sc, d, ctx->d_accum, ctx->d_stats, ctx->tune);
+        else k_raycast<false><<<persistent_grid(ctx, k_raycast<false>, nwork), 128, 0, st>>>(ctx->sc, d, ctx->d_accum, ctx->d_stats, ctx->tune);
         CU(cudaGetLastError()); nl++;
     } else {
         if (d.primary_reuse) {
-            const int block = 256; long long want = (nwork + block - 1) / block, cap = (long long)ctx->sm_count * 16;
-            const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-            if (count) k_primary<true><<<grid, block, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_stats);
-            else k_primary<false><<<grid, block, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_stats);
+            if (count) k_primary<true><<<persistent_grid(ctx, k_primary<true>, nwork), 128, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_stats, ctx->tune);
+            else k_primary<false><<<persistent_grid(ctx, k_primary<false>, nwork), 128, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_stats, ctx->tune);
             CU(cudaGetLastError()); nl++;
         }
         CU(cudaEventRecord(ctx->ev[1], st));
         // persistent lanes: as many CTAs as stay resident, all of them pulling pixels from one counter
-        int per_sm = 0;
-        if (count) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_paths<true>, 128, 0));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_paths<false>, 128, 0));
-        if (per_sm < 1) per_sm = 1;
-        long long grid = (long long)ctx->sm_count * per_sm, want = (nwork + 127) / 128;
-        if (want < grid) grid = want ? want : 1;
         const int2 *prim = d.primary_reuse ? ctx->d_prim : nullptr;
-        if (count) k_paths<true><<<(int)grid, 128, 0, st>>>(ctx->sc, d, prim, ctx->d_accum, ctx->d_stats);
-        else k_paths<false><<<(int)grid, 128, 0, st>>>(ctx->sc, d, prim, ctx->d_accum, ctx->d_stats);
+        if (count) k_paths<true><<<persistent_grid(ctx, k_paths<true>, nwork), 128, 0, st>>>(ctx->sc, d, prim, ctx->d_accum, ctx->d_stats, ctx->tune);
+        else k_paths<false><<<persistent_grid(ctx, k_paths<false>, nwork), 128, 0, st>>>(ctx->sc, d, prim, ctx->d_accum, ctx->d_stats, ctx->tune);
         CU(cudaGetLastError()); nl++;
     }
     CU(cudaEventRecord(ctx->ev[2], st));

@@ -62,7 +62,10 @@ constexpr uint32_t kLeaf = 0x80000000u;
 constexpr uint32_t kAxisShift = 28;
 constexpr uint32_t kCountMask = 0x0fffffffu;
 constexpr uint32_t kPhaseB = 0x80000000u;
-constexpr int kStackWords = 3 * 48 + 4;        // worst case: every frame parked in phase B (3 words)
+constexpr int kStackWords = 3 * 48 + 4;
+#ifndef SQT_MAX_DEPTH
+#define SQT_MAX_DEPTH 64
+#endif        // worst case: every frame parked in phase B (3 words)
 
 struct SceneView {
     const float4 *nodes;     // 3 float4 per branch
@@ -182,24 +185,6 @@ SQT_HD bool moller_trumbore(const float4 &a0, const float4 &a1, const float4 &a2
     return true;
 }
 
-// Leaf (BIH.hs:105-109): V.mapMaybe over the leaf's triangles, minimumBy (comparing dist).
-// base-4.9 minimumBy = foldr1 min' with min' x y = GT -> y ; _ -> x : walk from the last triangle
-// to the first, the earlier one wins unless it is strictly farther.
-template <bool COUNT>
-SQT_HD Hit leaf_test(const SceneView &sc, const Ray &r, uint32_t first, uint32_t count, Counters *cn) {
-    Hit best; best.tri = -1; best.t = 0.0f; best.dist = 0.0f;
-    if (COUNT) cn->tri_tests += count;
-    for (int i = (int)count - 1; i >= 0; --i) {
-        const float4 *p = sc.tris + 3 * (size_t)(first + (uint32_t)i);
-        float4 a0 = SQT_LDG4(p), a1 = SQT_LDG4(p + 1), a2 = SQT_LDG4(p + 2);
-        float t, dist;
-        if (moller_trumbore(a0, a1, a2, r, t, dist)) {
-            if (best.tri < 0 || !cmp_gt(dist, best.dist)) { best.tri = (int)(first + (uint32_t)i); best.t = t; best.dist = dist; }
-        }
-    }
-    return best;
-}
-
 // ------------------------------------------------------------------------------ traversal
 // intersectBIH (BIH.hs:101-141) as an explicit-stack state machine that visits exactly the
 // subtrees the recursion visits, in the same order, and combines results with the same rules:
@@ -209,73 +194,134 @@ SQT_HD Hit leaf_test(const SceneView &sc, const Ray &r, uint32_t first, uint32_t
 //     the near child; when that subtree returns, isClose (BIH.hs:121-123) is evaluated on the near
 //     subtree's OWN result; if the far child must still be visited and near had a hit, that hit is
 //     parked on the stack ("phase B", 3 words) and merged with min' when the far subtree returns.
+//
+// The machine is cut into three kinds of unit step so that a warp can run them in lock step
+// (sqt_backend.cu: all lanes do traversal steps together, then all lanes do triangle steps together):
+//   ST_DESC  enter subtree (child, meta): a Branch -> test both child boxes, pick the next subtree;
+//            a Leaf -> become ST_LEAF
+//   ST_LEAF  test ONE triangle of the current leaf, walking from the last to the first
+//   ST_RET   a subtree returned `cur`: pop ONE stack entry and act on it
+//   ST_DONE  the ray is finished, result in `cur`
+enum : int { ST_DONE = 0, ST_DESC = 1, ST_LEAF = 2, ST_RET = 3, ST_EXIT = 4 };
+
+struct TravLane {
+    Ray r;
+    float dfx, dfy, dfz;        // 1/dir (Geometry.hs:168), IEEE
+    uint32_t child, meta;       // ST_DESC: subtree to enter ; ST_LEAF: child = first triangle of the leaf
+    int i;                      // ST_LEAF: offset of the next triangle to test (counts down to 0)
+    Hit cur;                    // result of the subtree that just returned / running best of the current leaf
+    int sp;
+    int state;
+    bool safe;
+    uint32_t *stack;            // kStackWords words of lane-private (local) memory, owned by the caller
+};
+
+// intersectBIH b = intersectBIH' (bounds b) (tree b)   (BIH.hs:101-102)
+template <bool COUNT>
+SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
+    if (COUNT) cn->rays += 1;
+    L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
+    L.sp = 0;
+    if (sc.root_is_leaf) {                       // tree = Leaf: no box test at all (BIH.hs:105)
+        L.child = 0u; L.i = (int)sc.n_tris - 1;
+        L.state = sc.n_tris ? ST_LEAF : ST_DONE;
+        if (COUNT) cn->tri_tests += sc.n_tris;
+        return;
+    }
+    L.dfx = XRCP(L.r.dx); L.dfy = XRCP(L.r.dy); L.dfz = XRCP(L.r.dz);
+    L.safe = finite_f(L.dfx) && finite_f(L.dfy) && finite_f(L.dfz) && finite_f(L.r.dx) && finite_f(L.r.dy) &&
+             finite_f(L.r.dz) && finite_f(L.r.ox) && finite_f(L.r.oy) && finite_f(L.r.oz);
+    if (!slab_exact(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], L.r, L.dfx,
+                    L.dfy, L.dfz)) { L.state = ST_DONE; return; }          // BIH.hs:112 at the root
+    L.child = 0u; L.meta = 0u; L.state = ST_DESC;
+}
+
+template <bool COUNT>
+SQT_HD void enter_leaf(TravLane &L, Counters *cn) {
+    const uint32_t count = L.meta & kCountMask;
+    if (COUNT) cn->tri_tests += count;
+    L.cur.tri = -1;
+    L.i = (int)count - 1;
+    L.state = count ? ST_LEAF : ST_RET;          // empty leaf -> Nothing (BIH.hs:107)
+}
+
+template <bool COUNT>
+SQT_HD void desc_step(const SceneView &sc, TravLane &L, Counters *cn) {
+    if (L.meta & kLeaf) { enter_leaf<COUNT>(L, cn); return; }
+    const float4 *np = sc.nodes + 3 * (size_t)L.child;
+    const float4 q0 = SQT_LDG4(np), q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
+    const uint32_t left = f2u(q2.x), right = f2u(q2.y), lmeta = f2u(q2.z), rmeta = f2u(q2.w);
+    const int ax = (int)((lmeta >> kAxisShift) & 3u);
+    bool hit_l, hit_r;
+    slab_children(q0, q1, ax, L.r, L.dfx, L.dfy, L.dfz, L.safe, hit_l, hit_r);
+    if (COUNT) { cn->branch_visits += 1; cn->child_box_tests += 2; }
+    const bool ltr = sel3(ax, L.r.dx, L.r.dy, L.r.dz) > 0.0f;              // BIH.hs:127
+    const uint32_t lm = lmeta & ~(3u << kAxisShift);
+    if (hit_l && hit_r) {
+        L.stack[L.sp++] = L.child;                                          // phase A frame
+        if (ltr) { L.child = left; L.meta = lm; } else { L.child = right; L.meta = rmeta; }
+    } else if (hit_l) { L.child = left; L.meta = lm; }
+    else if (hit_r) { L.child = right; L.meta = rmeta; }
+    else { L.cur.tri = -1; L.state = ST_RET; return; }
+    if (L.meta & kLeaf) enter_leaf<COUNT>(L, cn);
+}
+
+// One triangle of the leaf (BIH.hs:105-109): V.mapMaybe over the leaf's triangles, minimumBy (comparing dist).
+// base-4.9 minimumBy = foldr1 min' with min' x y = GT -> y ; _ -> x : walk from the last triangle
+// to the first, the earlier one wins unless it is strictly farther.
+SQT_HD void tri_step(const SceneView &sc, TravLane &L) {
+    const uint32_t idx = L.child + (uint32_t)L.i;
+    const float4 *p = sc.tris + 3 * (size_t)idx;
+    const float4 a0 = SQT_LDG4(p), a1 = SQT_LDG4(p + 1), a2 = SQT_LDG4(p + 2);
+    float t, dist;
+    if (moller_trumbore(a0, a1, a2, L.r, t, dist)) {
+        if (L.cur.tri < 0 || !cmp_gt(dist, L.cur.dist)) { L.cur.tri = (int)idx; L.cur.t = t; L.cur.dist = dist; }
+    }
+    if (--L.i < 0) L.state = ST_RET;
+}
+
+SQT_HD void ret_step(const SceneView &sc, TravLane &L) {
+    if (L.sp == 0) { L.state = ST_DONE; return; }
+    const uint32_t top = L.stack[L.sp - 1];
+    if (top & kPhaseB) {                                                    // far subtree returned: min' near far
+        Hit rn; rn.tri = (int)(top & ~kPhaseB); rn.dist = u2f(L.stack[L.sp - 2]); rn.t = u2f(L.stack[L.sp - 3]);
+        L.sp -= 3;
+        if (L.cur.tri < 0 || !cmp_gt(rn.dist, L.cur.dist)) L.cur = rn;
+        return;
+    }
+    L.sp -= 1;                                                              // near subtree of branch `top` returned
+    const float4 *np = sc.nodes + 3 * (size_t)top;
+    const float4 q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
+    const uint32_t lmeta = f2u(q2.z);
+    const int ax = (int)((lmeta >> kAxisShift) & 3u);
+    const float d_ax = sel3(ax, L.r.dx, L.r.dy, L.r.dz);
+    const bool ltr = d_ax > 0.0f;
+    if (L.cur.tri >= 0) {
+        const float p = XADD(sel3(ax, L.r.ox, L.r.oy, L.r.oz), XMUL(L.cur.t, d_ax));   // intersectPoint on ax
+        const bool close = ltr ? (p < q1.w) : (p > q1.z);                   // BIH.hs:121-123
+        if (close) return;
+        L.stack[L.sp] = f2u(L.cur.t); L.stack[L.sp + 1] = f2u(L.cur.dist); L.stack[L.sp + 2] = (uint32_t)L.cur.tri | kPhaseB;
+        L.sp += 3;
+    }
+    if (ltr) { L.child = f2u(q2.y); L.meta = f2u(q2.w); }
+    else { L.child = f2u(q2.x); L.meta = lmeta & ~(3u << kAxisShift); }
+    L.state = ST_DESC;
+}
+
+// one lane alone, to completion (host emulation and the odd single ray)
 template <bool COUNT>
 SQT_HD Hit traverse(const SceneView &sc, const Ray &r, Counters *cn) {
-    Hit cur; cur.tri = -1; cur.t = 0.0f; cur.dist = 0.0f;
-    if (COUNT) cn->rays += 1;
-    if (sc.root_is_leaf) return leaf_test<COUNT>(sc, r, 0u, sc.n_tris, cn);
-    const float dfx = XRCP(r.dx), dfy = XRCP(r.dy), dfz = XRCP(r.dz);
-    const bool safe = finite_f(dfx) && finite_f(dfy) && finite_f(dfz) && finite_f(r.dx) && finite_f(r.dy) &&
-                      finite_f(r.dz) && finite_f(r.ox) && finite_f(r.oy) && finite_f(r.oz);
-    if (!slab_exact(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], r, dfx,
-                    dfy, dfz))
-        return cur;
     uint32_t stack[kStackWords];
-    int sp = 0;
-    uint32_t child = 0u, meta = 0u;
-    for (;;) {
-        bool have = true;
-        // ---- descend: branch visits until a leaf is reached or both children are missed
-        while (!(meta & kLeaf)) {
-            const float4 *np = sc.nodes + 3 * (size_t)child;
-            const float4 q0 = SQT_LDG4(np), q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
-            const uint32_t left = f2u(q2.x), right = f2u(q2.y), lmeta = f2u(q2.z), rmeta = f2u(q2.w);
-            const int ax = (int)((lmeta >> kAxisShift) & 3u);
-            bool hit_l, hit_r;
-            slab_children(q0, q1, ax, r, dfx, dfy, dfz, safe, hit_l, hit_r);
-            if (COUNT) { cn->branch_visits += 1; cn->child_box_tests += 2; }
-            const bool ltr = sel3(ax, r.dx, r.dy, r.dz) > 0.0f;          // BIH.hs:127
-            if (hit_l && hit_r) {
-                stack[sp++] = child;                                      // phase A frame
-                if (ltr) { child = left; meta = lmeta & ~(3u << kAxisShift); }
-                else { child = right; meta = rmeta; }
-            } else if (hit_l) { child = left; meta = lmeta & ~(3u << kAxisShift); }
-            else if (hit_r) { child = right; meta = rmeta; }
-            else { have = false; break; }
-        }
-        if (have) cur = leaf_test<COUNT>(sc, r, child, meta & kCountMask, cn);
-        else { cur.tri = -1; }
-        // ---- unwind
-        bool resume = false;
-        while (sp > 0) {
-            const uint32_t top = stack[sp - 1];
-            if (top & kPhaseB) {                                          // far subtree returned: min' near far
-                Hit rn; rn.tri = (int)(top & ~kPhaseB); rn.dist = u2f(stack[sp - 2]); rn.t = u2f(stack[sp - 3]);
-                sp -= 3;
-                if (cur.tri < 0 || !cmp_gt(rn.dist, cur.dist)) cur = rn;
-                continue;
-            }
-            sp -= 1;                                                      // near subtree of branch `top` returned
-            const float4 *np = sc.nodes + 3 * (size_t)top;
-            const float4 q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
-            const uint32_t lmeta = f2u(q2.z);
-            const int ax = (int)((lmeta >> kAxisShift) & 3u);
-            const float d_ax = sel3(ax, r.dx, r.dy, r.dz);
-            const bool ltr = d_ax > 0.0f;
-            if (cur.tri >= 0) {
-                const float p = XADD(sel3(ax, r.ox, r.oy, r.oz), XMUL(cur.t, d_ax));   // intersectPoint on ax
-                const bool close = ltr ? (p < q1.w) : (p > q1.z);         // BIH.hs:121-123
-                if (close) continue;
-                stack[sp] = f2u(cur.t); stack[sp + 1] = f2u(cur.dist); stack[sp + 2] = (uint32_t)cur.tri | kPhaseB;
-                sp += 3;
-            }
-            if (ltr) { child = f2u(q2.y); meta = f2u(q2.w); }
-            else { child = f2u(q2.x); meta = lmeta & ~(3u << kAxisShift); }
-            resume = true;
-            break;
-        }
-        if (!resume) return cur;
+    TravLane L;
+    L.stack = stack;
+    L.r = r;
+    start_ray<COUNT>(sc, L, cn);
+    while (L.state != ST_DONE) {
+        if (L.state == ST_RET) ret_step(sc, L);
+        if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
+        if (L.state == ST_LEAF) tri_step(sc, L);
     }
+    return L.cur;
 }
 
 // ------------------------------------------------------------------------------------- RNG
@@ -305,22 +351,6 @@ SQT_HD float random_r01(uint32_t n) {
 #else
     return XMUL((float)n, 2.3283064365386963e-10f);
 #endif
-}
-
-struct DrawCache {          // the four draws of one Philox block of the current sample
-    uint32_t w[4];
-    int block;              // -1 = empty
-};
-SQT_HD float draw(DrawCache &dc, uint64_t seed, uint64_t stream, uint32_t j) {
-    const int b = (int)(j >> 2);
-    if (b != dc.block) {
-        philox4x32_10((uint32_t)stream, (uint32_t)(stream >> 32), (uint32_t)b, 0x52545153u, (uint32_t)seed,
-                      (uint32_t)(seed >> 32), dc.w);
-        dc.block = b;
-    }
-    const uint32_t k = j & 3u;
-    const uint32_t w = k == 0 ? dc.w[0] : (k == 1 ? dc.w[1] : (k == 2 ? dc.w[2] : dc.w[3]));
-    return random_r01(w);
 }
 
 // ------------------------------------------------------------------------------------ trig
@@ -399,11 +429,10 @@ SQT_HD Ray make_ray(const RenderParams &p, int y, int x) {
 
 SQT_HD float hs_signum(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : x); }
 
-// bounceRay (Lib.hs:155-160) at a hit on triangle `tri` (leaf order) with hit parameter t:
-// x = draw j decides scatter/reflect; scatter reuses x as the azimuth draw and takes draw j+1 as the
-// polar draw.  Returns the new ray; origin = intersectPoint = o + t*^d.
-SQT_HD Ray bounce_ray(const SceneView &sc, const Ray &in, int tri, float t, float reflective, DrawCache &dc,
-                      unsigned long long seed, unsigned long long stream, uint32_t j) {
+// bounceRay (Lib.hs:155-160) at a hit on triangle `tri` (leaf order) with hit parameter t.  The caller
+// drew x = draw j (scatter iff reflective < x) and, for a scatter, v = draw j+1: scatter reuses x as the
+// azimuth draw and takes v as the polar draw.  Returns the new ray; origin = intersectPoint.
+SQT_HD Ray bounce_ray(const SceneView &sc, const Ray &in, int tri, float t, bool scatter, float x, float v) {
     const float4 *p = sc.tris + 3 * (size_t)tri;
     const float4 a0 = SQT_LDG4(p), a1 = SQT_LDG4(p + 1), a2 = SQT_LDG4(p + 2);
     const float e1x = a0.w, e1y = a1.x, e1z = a1.y, e2x = a1.z, e2y = a1.w, e2z = a2.x;
@@ -413,9 +442,7 @@ SQT_HD Ray bounce_ray(const SceneView &sc, const Ray &in, int tri, float t, floa
     const float nz = XSUB(XMUL(e1x, e2y), XMUL(e1y, e2x));
     Ray out;
     out.ox = XADD(in.ox, XMUL(t, in.dx)); out.oy = XADD(in.oy, XMUL(t, in.dy)); out.oz = XADD(in.oz, XMUL(t, in.dz));
-    const float x = draw(dc, seed, stream, j);
-    if (reflective < x) {                       // scatterRay, Lib.hs:166-172 ; randomVector Lib.hs:192-198
-        const float v = draw(dc, seed, stream, j + 1u);
+    if (scatter) {                              // scatterRay, Lib.hs:166-172 ; randomVector Lib.hs:192-198
         const float th = XMUL(6.28318530717958647692f, x);             // 2 * pi * u
         const float ph = sqt_acos(XSUB(XMUL(2.0f, v), 1.0f));
         float sth, cth, sph, cph;

@@ -1,12 +1,20 @@
-// sqt_paths.cuh -- the per-lane integrator loop (renderPixel / raytrace / raycast, Lib.hs:79-151).
+// sqt_paths.cuh -- what a lane does BETWEEN rays: the integrator (renderPixel / raytrace / raycast,
+// Lib.hs:79-151) and the two simpler ray sources (batched intersect, primary hits), written as "policies"
+// with one entry point:
 //
-// One lane owns one pixel at a time and runs its samples k = k0..k1-1 in order, so the per-pixel
-// radiance sum is the reference's sequential `sum = foldl (+) 0` (Lib.hs:88).  A lane whose path ends
-// (miss, depth cut, black surface) immediately starts its next sample -- or fetches its next pixel --
-// inside the inner "until I have a ray" loop, so that every lane enters the traversal with a live ray
-// (path regeneration; keeps warps full although path lengths differ).
+//     regen(sc, L, cn)   called when L.state == ST_DONE: consume the hit in L.cur (if a ray was in flight),
+//                        then put the lane's next ray into L.r and start it -- or set ST_EXIT when the lane
+//                        has no more work.
 //
-// SQT_HD like sqt_core.cuh: tests/emu compiles it for the host, the product only runs it on the device.
+// The kernels in sqt_backend.cu run one warp-synchronous loop around these: regen for lanes that are done,
+// traversal steps for lanes that are descending/returning, triangle steps for lanes inside a leaf
+// (sqt_core.cuh).  Lanes are independent, so any schedule yields the same per-lane results; tests/emu runs
+// each lane to completion on the host with the same functions.
+//
+// Integrator layout: one lane owns one pixel at a time and runs its samples k = k0..k1-1 in order, so the
+// per-pixel radiance sum is the reference's sequential `sum = foldl (+) 0` (Lib.hs:88).  A lane whose path
+// ends (miss, depth cut, black surface) starts its next sample -- or fetches its next pixel -- right away
+// (path regeneration), so lanes re-enter the traversal with a live ray.
 #pragma once
 #include "sqt_core.cuh"
 
@@ -37,6 +45,9 @@ SQT_HD void sample_range(const RenderParams &p, int &k0, int &k1) {
     }
 }
 
+constexpr uint32_t kMatEmits = 1u;       // emissive *^ emitColor != 0
+constexpr uint32_t kMatBlack = 2u;       // surfColor == (0,0,0)
+
 // radiance of one finished path: L_j = surfColor_j * L_{j+1} + emissive_j *^ emitColor_j, evaluated from
 // the deepest shaded bounce outwards exactly like the recursion of Lib.hs:135-137 (L beyond the end = black).
 SQT_HD void fold_path(const SceneView &sc, const uint16_t *pm, int last, float &lr, float &lg, float &lb) {
@@ -50,32 +61,51 @@ SQT_HD void fold_path(const SceneView &sc, const uint16_t *pm, int last, float &
     }
 }
 
-constexpr uint32_t kMatEmits = 1u;       // emissive *^ emitColor != 0
-constexpr uint32_t kMatBlack = 2u;       // surfColor == (0,0,0)
-
+// ------------------------------------------------------------------------------- raytrace policy
 // Fetch: functor returning the next work item (>= 0) or -1 when the queue is empty.
-// prim: per pixel (tri, t bits) of the primary hit, or nullptr when primary reuse is off.
-template <bool COUNT, class Fetch>
-SQT_HD_NOINLINE void render_lane(const SceneView &sc, const RenderParams &p, const int2 *prim, float *accum,
-                                 Fetch &fetch, Counters *cn, PathStats &st) {
-    int k0, k1;
-    sample_range(p, k0, k1);
-    uint16_t pm[64];                     // material of every shaded bounce of the current path
-    DrawCache dc; dc.block = -1;
-    dc.w[0] = dc.w[1] = dc.w[2] = dc.w[3] = 0u;
+template <class Fetch>
+struct PathPolicy {
+    const RenderParams &p;
+    const int2 *prim;          // per pixel (tri, t bits) of the primary hit, or nullptr when primary reuse is off
+    float *accum;
+    Fetch &fetch;
+    PathStats &st;
+    // per-lane path state
     long long pixel = -1;
-    int k = 0, j = 0;                    // sample index, bounce index of the hit being shaded
-    int ptri = -1; float pt = 0.0f;      // primary hit of the current pixel
-    Ray pr;                              // primary ray of the current pixel
-    pr.ox = pr.oy = pr.oz = pr.dx = pr.dy = pr.dz = 0.0f;
-    Ray ray = pr, nr = pr;               // ray that produced the current hit ; ray to trace next
-    int htri = -1; float ht = 0.0f;      // current hit
+    int k = 0, k0 = 0, k1 = 0, j = 0;        // sample index / range, bounce index of the hit being shaded
+    int ptri = -1; float pt = 0.0f;          // cached primary hit of the current pixel
+    int px = 0, py = 0;
     unsigned long long rix = 0ull;
     float sr = 0.0f, sg = 0.0f, sb = 0.0f;
-    bool any_emit = false, have_ray = false, path_over = false, need_pixel = true, start = false, done = false;
+    float saved_r = 0.0f; int saved_j = -1;  // draw j+1 of a scatter is draw j of the next bounce
+    bool any_emit = false, in_flight = false, need_pixel = true;
+    uint16_t *pm;                            // SQT_MAX_DEPTH entries of lane-private memory: material of every
+                                             // shaded bounce of the current path
 
-    for (;;) {
-        while (!have_ray) {
+    SQT_HD PathPolicy(const RenderParams &p_, const int2 *prim_, float *accum_, Fetch &f_, PathStats &st_, uint16_t *pm_)
+        : p(p_), prim(prim_), accum(accum_), fetch(f_), st(st_), pm(pm_) { sample_range(p, k0, k1); }
+
+    SQT_HD float draw_r(uint32_t jj) {
+        if ((int)jj == saved_j) return saved_r;
+        uint32_t w[4];
+        const unsigned long long stream = rix + (unsigned long long)k;
+        philox4x32_10((uint32_t)stream, (uint32_t)(stream >> 32), jj >> 2, 0x52545153u, (uint32_t)p.seed,
+                      (uint32_t)(p.seed >> 32), w);
+        const uint32_t q = jj & 3u;
+        return random_r01(q == 0 ? w[0] : (q == 1 ? w[1] : (q == 2 ? w[2] : w[3])));
+    }
+
+    template <bool COUNT>
+    SQT_HD void regen(const SceneView &sc, TravLane &L, Counters *cn) {
+        bool path_over = false, start = false;
+        int htri = -1; float ht = 0.0f;
+        if (in_flight) {                                  // the ray of Lib.hs:131 came back
+            in_flight = false;
+            st.rays += 1;
+            if (L.cur.tri >= 0) { htri = L.cur.tri; ht = L.cur.t; j += 1; }
+            else path_over = true;
+        }
+        for (;;) {
             if (path_over) {
                 // ---- finish sample k: add its radiance, in sample order (Lib.hs:87-88)
                 if (any_emit) {
@@ -92,15 +122,13 @@ SQT_HD_NOINLINE void render_lane(const SceneView &sc, const RenderParams &p, con
             }
             if (need_pixel) {
                 const long long w = fetch();
-                if (w < 0) { done = true; break; }
+                if (w < 0) { L.state = ST_EXIT; return; }
                 pixel = work_to_pixel(p, w);
-                if (pixel < 0) continue;
-                const int y = (int)(pixel / p.cols), x = (int)(pixel % p.cols);
-                pr = make_ray(p, y, x);
-                rix = (unsigned long long)p.spp * ((unsigned long long)x + (unsigned long long)y * (unsigned long long)p.seed_stride);
+                if (pixel < 0 || k0 >= k1) continue;
+                py = (int)(pixel / p.cols); px = (int)(pixel % p.cols);
+                rix = (unsigned long long)p.spp * ((unsigned long long)px + (unsigned long long)py * (unsigned long long)p.seed_stride);
                 sr = sg = sb = 0.0f;
                 k = k0;
-                if (k0 >= k1) continue;
                 if (prim) {
                     const int2 ph = prim[pixel];
                     ptri = ph.x; pt = u2f((uint32_t)ph.y);
@@ -117,11 +145,12 @@ SQT_HD_NOINLINE void render_lane(const SceneView &sc, const RenderParams &p, con
                 // A sample begins at the cached primary hit (bounce 0 already intersected: the primary ray is
                 // the same for every sample of a pixel, Lib.hs:81) or, with primary reuse off, by tracing the
                 // primary ray again like Lib.hs:84 does.
-                start = false; any_emit = false; dc.block = -1;
-                if (prim) { ray = pr; htri = ptri; ht = pt; j = 0; st.primary_reused += 1; }
-                else { nr = pr; j = -1; have_ray = true; continue; }
+                start = false; any_emit = false; saved_j = -1;
+                L.r = make_ray(p, py, px);
+                if (prim) { htri = ptri; ht = pt; j = 0; st.primary_reused += 1; }
+                else { j = -1; in_flight = true; start_ray<COUNT>(sc, L, cn); return; }
             }
-            // ---- shade the hit of bounce j (raytrace, Lib.hs:127-137)
+            // ---- shade the hit of bounce j (raytrace, Lib.hs:127-137); L.r is the ray that produced it
             const float4 *tp = sc.tris + 3 * (size_t)htri;
             const uint32_t mat = f2u(SQT_LDG4(tp + 2).y);
             pm[j] = (uint16_t)mat;
@@ -130,52 +159,167 @@ SQT_HD_NOINLINE void render_lane(const SceneView &sc, const RenderParams &p, con
             const uint32_t mflags = f2u(SQT_LDG4(mp + 2).w);
             any_emit = any_emit || (mflags & kMatEmits);
             const bool terminal = (j + 1 > p.max_depth - 1) || (p.terminate_on_black && (mflags & kMatBlack));
-            if (!terminal) {
-                nr = bounce_ray(sc, ray, htri, ht, m0.x, dc, p.seed, rix + (unsigned long long)k, (uint32_t)j);
-                have_ray = true;
-            } else path_over = true;
+            if (terminal) { path_over = true; continue; }
+            // bounceRay (Lib.hs:155-160)
+            const float x = draw_r((uint32_t)j);
+            float v = 0.0f;
+            const bool scatter = m0.x < x;
+            if (scatter) { v = draw_r((uint32_t)j + 1u); saved_r = v; saved_j = j + 1; } else saved_j = -1;
+            L.r = bounce_ray(sc, L.r, htri, ht, scatter, x, v);
+            in_flight = true;
+            start_ray<COUNT>(sc, L, cn);
+            return;
         }
-        if (done) break;
-        // ---- trace one segment (Lib.hs:131)
-        const Hit h = traverse<COUNT>(sc, nr, cn);
-        st.rays += 1;
-        have_ray = false;
-        if (h.tri >= 0) { ray = nr; htri = h.tri; ht = h.t; j += 1; }
-        else path_over = true;
     }
-}
+};
 
-// --cast (Lib.hs:141-151): primary hit + one shadow ray to the hard-coded light; every sample identical.
-template <bool COUNT>
-SQT_HD void raycast_pixel(const SceneView &sc, const RenderParams &p, long long pixel, float *accum, Counters *cn,
-                          PathStats &st) {
-    const int y = (int)(pixel / p.cols), x = (int)(pixel % p.cols);
-    const Ray r = make_ray(p, y, x);
-    int k0, k1;
-    sample_range(p, k0, k1);
-    float cr = 0.0f, cg = 0.0f, cb = 0.0f;
-    const Hit h = traverse<COUNT>(sc, r, cn);
-    st.rays += 1;
-    if (h.tri >= 0) {
-        const float px = XADD(r.ox, XMUL(h.t, r.dx)), py = XADD(r.oy, XMUL(h.t, r.dy)), pz = XADD(r.oz, XMUL(h.t, r.dz));
-        Ray s;                                                   // a `to` b = Ray a (b - a), light = V3 0 3 (-1)
-        s.ox = px; s.oy = py; s.oz = pz;
-        s.dx = XSUB(0.0f, px); s.dy = XSUB(3.0f, py); s.dz = XSUB(-1.0f, pz);
-        const float ex = XSUB(px, 0.0f), ey = XSUB(py, 3.0f), ez = XSUB(pz, -1.0f);
-        const float dl = XSQRT(dot3(ex, ey, ez, ex, ey, ez));
-        const Hit sh = traverse<COUNT>(sc, s, cn);
-        st.rays += 1;
-        if (!(sh.tri >= 0 && !(sh.dist > dl))) {
-            const uint32_t mat = f2u(SQT_LDG4(sc.tris + 3 * (size_t)h.tri + 2).y);
+// ------------------------------------------------------------------------------- batched intersect policy
+// Scene.intersect over a ray batch (Geometry.hs:64): lane takes rays idx, idx + stride, ...
+struct BatchPolicy {
+    const float *org, *dir;
+    long long n, idx, stride;
+    int *tri_out; float *dist_out, *point_out;
+    PathStats &st;
+    bool in_flight = false;
+    SQT_HD BatchPolicy(const float *o, const float *d, long long n_, long long first, long long stride_, int *t, float *di,
+                       float *po, PathStats &st_)
+        : org(o), dir(d), n(n_), idx(first), stride(stride_), tri_out(t), dist_out(di), point_out(po), st(st_) {}
+
+    template <bool COUNT>
+    SQT_HD void regen(const SceneView &sc, TravLane &L, Counters *cn) {
+        if (in_flight) {
+            in_flight = false;
+            st.rays += 1;
+            const bool hit = L.cur.tri >= 0;
+            tri_out[idx] = hit ? (int)f2u(SQT_LDG4(sc.tris + 3 * (size_t)L.cur.tri + 2).z) : -1;
+            if (dist_out) dist_out[idx] = hit ? L.cur.dist : 0.0f;
+            if (point_out) {
+                point_out[3 * idx] = hit ? XADD(L.r.ox, XMUL(L.cur.t, L.r.dx)) : 0.0f;
+                point_out[3 * idx + 1] = hit ? XADD(L.r.oy, XMUL(L.cur.t, L.r.dy)) : 0.0f;
+                point_out[3 * idx + 2] = hit ? XADD(L.r.oz, XMUL(L.cur.t, L.r.dz)) : 0.0f;
+            }
+            idx += stride;
+        }
+        if (idx >= n) { L.state = ST_EXIT; return; }
+        L.r.ox = org[3 * idx]; L.r.oy = org[3 * idx + 1]; L.r.oz = org[3 * idx + 2];
+        L.r.dx = dir[3 * idx]; L.r.dy = dir[3 * idx + 1]; L.r.dz = dir[3 * idx + 2];
+        in_flight = true;
+        start_ray<COUNT>(sc, L, cn);
+    }
+};
+
+// ------------------------------------------------------------------------------- primary-hit policy
+// makeRay (Lib.hs:107-114) + closest hit for every owned pixel, cached as (tri, t bits)
+struct PrimaryPolicy {
+    const RenderParams &p;
+    int2 *prim;
+    long long nwork, w, stride, pixel = -1;
+    PathStats &st;
+    bool in_flight = false;
+    SQT_HD PrimaryPolicy(const RenderParams &p_, int2 *prim_, long long nwork_, long long first, long long stride_, PathStats &st_)
+        : p(p_), prim(prim_), nwork(nwork_), w(first), stride(stride_), st(st_) {}
+
+    template <bool COUNT>
+    SQT_HD void regen(const SceneView &sc, TravLane &L, Counters *cn) {
+        if (in_flight) {
+            in_flight = false;
+            st.rays += 1;
+            int2 h; h.x = L.cur.tri; h.y = (int)f2u(L.cur.t);
+            prim[pixel] = h;
+            w += stride;
+        }
+        for (;;) {
+            if (w >= nwork) { L.state = ST_EXIT; return; }
+            pixel = work_to_pixel(p, w);
+            if (pixel >= 0) break;
+            w += stride;
+        }
+        L.r = make_ray(p, (int)(pixel / p.cols), (int)(pixel % p.cols));
+        in_flight = true;
+        start_ray<COUNT>(sc, L, cn);
+    }
+};
+
+// ------------------------------------------------------------------------------- --cast policy
+// raycast (Lib.hs:141-151): primary hit + one shadow ray to the hard-coded light; every sample identical.
+struct CastPolicy {
+    const RenderParams &p;
+    float *accum;
+    long long nwork, w, stride, pixel = -1;
+    PathStats &st;
+    int stage = 0;                 // 0 idle, 1 primary in flight, 2 shadow in flight
+    int htri = -1; float dl = 0.0f;
+    SQT_HD CastPolicy(const RenderParams &p_, float *accum_, long long nwork_, long long first, long long stride_, PathStats &st_)
+        : p(p_), accum(accum_), nwork(nwork_), w(first), stride(stride_), st(st_) {}
+
+    SQT_HD void finish(const SceneView &sc, bool lit) {
+        float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+        if (lit) {
+            const uint32_t mat = f2u(SQT_LDG4(sc.tris + 3 * (size_t)htri + 2).y);
             const float4 m0 = SQT_LDG4(sc.mats + 3 * (size_t)mat);
-            const float kk = XDIV(2.0f, dl);
+            const float kk = XDIV(2.0f, dl);                        // (2 / distanceToLight) *^ surfColor
             cr = XMUL(kk, m0.y); cg = XMUL(kk, m0.z); cb = XMUL(kk, m0.w);
         }
+        int k0, k1;
+        sample_range(p, k0, k1);
+        float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+        for (int k = k0; k < k1; ++k) { sr = XADD(sr, cr); sg = XADD(sg, cg); sb = XADD(sb, cb); }
+        st.samples += (unsigned long long)(k1 > k0 ? k1 - k0 : 0);
+        accum[3 * pixel] = sr; accum[3 * pixel + 1] = sg; accum[3 * pixel + 2] = sb;
+        w += stride;
+        stage = 0;
     }
-    float sr = 0.0f, sg = 0.0f, sb = 0.0f;
-    for (int k = k0; k < k1; ++k) { sr = XADD(sr, cr); sg = XADD(sg, cg); sb = XADD(sb, cb); }
-    st.samples += (unsigned long long)(k1 > k0 ? k1 - k0 : 0);
-    accum[3 * pixel] = sr; accum[3 * pixel + 1] = sg; accum[3 * pixel + 2] = sb;
+
+    template <bool COUNT>
+    SQT_HD void regen(const SceneView &sc, TravLane &L, Counters *cn) {
+        if (stage == 1) {
+            st.rays += 1;
+            if (L.cur.tri < 0) finish(sc, false);
+            else {
+                htri = L.cur.tri;
+                const float hx = XADD(L.r.ox, XMUL(L.cur.t, L.r.dx)), hy = XADD(L.r.oy, XMUL(L.cur.t, L.r.dy)),
+                            hz = XADD(L.r.oz, XMUL(L.cur.t, L.r.dz));
+                // shadowRay = intersectPoint `to` hardCodedLight, light = V3 0 3 (-1) ; a `to` b = Ray a (b - a)
+                const float ex = XSUB(hx, 0.0f), ey = XSUB(hy, 3.0f), ez = XSUB(hz, -1.0f);
+                dl = XSQRT(dot3(ex, ey, ez, ex, ey, ez));
+                L.r.ox = hx; L.r.oy = hy; L.r.oz = hz;
+                L.r.dx = XSUB(0.0f, hx); L.r.dy = XSUB(3.0f, hy); L.r.dz = XSUB(-1.0f, hz);
+                stage = 2;
+                start_ray<COUNT>(sc, L, cn);
+                return;
+            }
+        } else if (stage == 2) {
+            st.rays += 1;
+            // guard $ maybe True (\pos -> dist pos > distanceToLight) (isect geom shadowRay)
+            finish(sc, !(L.cur.tri >= 0 && !(L.cur.dist > dl)));
+        }
+        for (;;) {
+            if (w >= nwork) { L.state = ST_EXIT; return; }
+            pixel = work_to_pixel(p, w);
+            if (pixel >= 0) break;
+            w += stride;
+        }
+        L.r = make_ray(p, (int)(pixel / p.cols), (int)(pixel % p.cols));
+        stage = 1;
+        start_ray<COUNT>(sc, L, cn);
+    }
+};
+
+// One lane, run to completion on its own (tests/emu; lanes are independent so this equals any warp schedule).
+template <bool COUNT, class Policy>
+SQT_HD_NOINLINE void run_lane(const SceneView &sc, Policy &pol, Counters *cn) {
+    uint32_t stack[kStackWords];
+    TravLane L;
+    L.stack = stack;
+    L.state = ST_DONE; L.sp = 0; L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
+    L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
+    for (;;) {
+        if (L.state == ST_DONE) pol.template regen<COUNT>(sc, L, cn);
+        if (L.state == ST_EXIT) break;
+        if (L.state == ST_RET) ret_step(sc, L);
+        if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
+        if (L.state == ST_LEAF) tri_step(sc, L);
+    }
 }
 
 }  // namespace sqt

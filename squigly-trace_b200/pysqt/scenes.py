@@ -1,0 +1,98 @@
+"""Seeded synthetic scenes for BASELINE.json configs 3-5 (numpy only; harness, not hot path).
+
+Each generator returns (v9, mat_idx, mats8): triangles as 9 floats in scene space, a material index per
+triangle, and materials as (reflective, surf rgb, emissive, emit rgb) rows -- the same shape of data
+trisFromObj (Obj.hs:49) yields.
+"""
+import numpy as np
+
+
+def _quad_grid(p0, du, dv, nu, nv):
+    """nu x nv cells over the parallelogram p0 + s*du + t*dv -> (2*nu*nv, 9) triangles."""
+    s = np.linspace(0.0, 1.0, nu + 1, dtype=np.float64)
+    t = np.linspace(0.0, 1.0, nv + 1, dtype=np.float64)
+    P = (np.asarray(p0, np.float64)[None, None, :] + s[:, None, None] * np.asarray(du, np.float64)[None, None, :]
+         + t[None, :, None] * np.asarray(dv, np.float64)[None, None, :])
+    a, b, c, d = P[:-1, :-1], P[1:, :-1], P[1:, 1:], P[:-1, 1:]
+    t1 = np.concatenate([a, b, c], -1).reshape(-1, 9)
+    t2 = np.concatenate([a, c, d], -1).reshape(-1, 9)
+    return np.concatenate([t1, t2]).astype(np.float32)
+
+
+def _box(lo, hi, n):
+    lo = np.asarray(lo, np.float64); hi = np.asarray(hi, np.float64); d = hi - lo
+    ex, ey, ez = np.array([d[0], 0, 0]), np.array([0, d[1], 0]), np.array([0, 0, d[2]])
+    faces = [(lo, ex, ey), (lo + ez, ex, ey), (lo, ex, ez), (lo + ey, ex, ez), (lo, ey, ez), (lo + ex, ey, ez)]
+    return np.concatenate([_quad_grid(p, u, v, n, n) for p, u, v in faces])
+
+
+def cornell_box(target_tris=10000, seed=0x5171):
+    """Config 3: open-front box x,z in [-2,2], y in [-2,2] (camera looks down -y from y=7 like data/camera),
+    one emissive quad under the ceiling, walls with reflective in {0, 0.2, 1}, two floor-standing boxes."""
+    n = max(2, int(round(np.sqrt(target_tris / (2.0 * (5 + 12 * 0.25))))))
+    m = max(1, n // 2)
+    parts, mats_idx = [], []
+
+    def add(tris, mat):
+        parts.append(tris); mats_idx.append(np.full(len(tris), mat, np.int32))
+    add(_quad_grid([-2, -2, -2], [4, 0, 0], [0, 4, 0], n, n), 0)      # floor (z=-2), diffuse grey
+    add(_quad_grid([-2, -2, 2], [4, 0, 0], [0, 4, 0], n, n), 0)       # ceiling
+    add(_quad_grid([-2, -2, -2], [4, 0, 0], [0, 0, 4], n, n), 1)      # back wall (y=-2), 0.2 reflective
+    add(_quad_grid([-2, -2, -2], [0, 4, 0], [0, 0, 4], n, n), 2)      # left wall (x=-2), red 0.2
+    add(_quad_grid([2, -2, -2], [0, 4, 0], [0, 0, 4], n, n), 3)       # right wall (x=2), mirror
+    add(_box([-1.3, -1.2, -2.0], [-0.3, -0.2, 0.4], m), 4)            # tall box, diffuse
+    add(_box([0.3, -0.3, -2.0], [1.3, 0.7, -0.9], m), 5)              # short box, mirror-ish
+    add(_quad_grid([-0.5, -0.5, 1.98], [1, 0, 0], [0, 1, 0], 1, 1), 6)  # light
+    mats = np.array([
+        [0.0, 0.73, 0.73, 0.73, 0, 0, 0, 0],
+        [0.2, 0.60, 0.60, 0.60, 0, 0, 0, 0],
+        [0.2, 0.63, 0.065, 0.05, 0, 0, 0, 0],
+        [1.0, 0.90, 0.90, 0.90, 0, 0, 0, 0],
+        [0.0, 0.14, 0.45, 0.091, 0, 0, 0, 0],
+        [1.0, 0.80, 0.80, 0.80, 0, 0, 0, 0],
+        [0.0, 0.0, 0.0, 0.0, 100, 1, 1, 1],
+    ], np.float32)
+    return np.concatenate(parts), np.concatenate(mats_idx), mats
+
+
+def subdivided_mesh(target_tris=1_000_000, seed=0x5172):
+    """Config 4: a jittered height-field mesh (deep BIH, traversal bound) over x,z... in [-2,2]^2 with an
+    emissive quad above it and diffuse material."""
+    rng = np.random.default_rng(seed)
+    n = max(2, int(round(np.sqrt(target_tris / 2.0))))
+    xs = np.linspace(-2, 2, n + 1); ys = np.linspace(-2, 2, n + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    edge = 4.0 / n
+    Z = (-1.0 + 0.35 * np.sin(2.3 * X) * np.cos(1.7 * Y) + 0.15 * np.sin(9.1 * X + 1.0) * np.sin(7.7 * Y)
+         + rng.uniform(-1e-3, 1e-3, X.shape) * edge)
+    X = X + rng.uniform(-1e-3, 1e-3, X.shape) * edge
+    Y = Y + rng.uniform(-1e-3, 1e-3, X.shape) * edge
+    P = np.stack([X, Y, Z], -1)
+    a, b, c, d = P[:-1, :-1], P[1:, :-1], P[1:, 1:], P[:-1, 1:]
+    tris = np.concatenate([np.concatenate([a, b, c], -1).reshape(-1, 9), np.concatenate([a, c, d], -1).reshape(-1, 9)])
+    light = _quad_grid([-0.7, -0.7, 1.9], [1.4, 0, 0], [0, 1.4, 0], 1, 1)
+    v9 = np.concatenate([tris.astype(np.float32), light])
+    mi = np.concatenate([np.zeros(len(tris), np.int32), np.ones(len(light), np.int32)])
+    mats = np.array([[0.0, 0.7, 0.7, 0.7, 0, 0, 0, 0], [0.0, 0, 0, 0, 100, 1, 1, 1]], np.float32)
+    return v9, mi, mats
+
+
+def triangle_soup(n_tris=10_000_000, seed=0x5173, all_reflective=True):
+    """Config 5: centroids ~U([-1,1]^3), edge length ~U(0.002,0.02), random orientation, materials reflective=1,
+    one in 64 triangles emissive."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, (n_tris, 3))
+    L = rng.uniform(0.002, 0.02, (n_tris, 1))
+    e = rng.normal(size=(n_tris, 3, 3))
+    e /= np.linalg.norm(e, axis=-1, keepdims=True)
+    v = c[:, None, :] + e * L[:, None, :] * 0.5
+    v9 = v.reshape(n_tris, 9).astype(np.float32)
+    mi = (rng.integers(0, 64, n_tris) == 0).astype(np.int32)
+    r = 1.0 if all_reflective else 0.3
+    mats = np.array([[r, 0.9, 0.9, 0.9, 0, 0, 0, 0], [r, 0.9, 0.9, 0.9, 20, 1, 0.9, 0.8]], np.float32)
+    return v9, mi, mats
+
+
+def soup_camera():
+    """Camera for the synthetic scenes: same pose convention as data/camera (position + rotMatrixRads output)."""
+    return None

@@ -4,6 +4,7 @@
 // this file runs the very same code on the CPU, lane by lane, so that `-m "not gpu"` tests can compare it
 // with the independent oracle (oracle/oracle.c) before any GPU time is spent.  It is NOT a fallback: the
 // product library (libsqt_b200.so) neither links nor loads it, and it lives under tests/.
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -46,20 +47,15 @@ int emu_height(emu_scene *s) { return (int)s->lay.height; }
 void emu_intersect_batch(emu_scene *s, const float *org, const float *dir, long long n, int *tri_out, float *dist_out,
                          float *point_out, unsigned long long *counters4) {
     Counters cn = {0, 0, 0, 0};
-    for (long long i = 0; i < n; ++i) {
-        Ray r{org[3 * i], org[3 * i + 1], org[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
-        const Hit h = traverse<true>(s->view, r, &cn);
-        const bool hit = h.tri >= 0;
-        tri_out[i] = hit ? (int)f2u(s->tris[3 * (size_t)h.tri + 2].z) : -1;
-        dist_out[i] = hit ? h.dist : 0.0f;
-        point_out[3 * i] = hit ? XADD(r.ox, XMUL(h.t, r.dx)) : 0.0f;
-        point_out[3 * i + 1] = hit ? XADD(r.oy, XMUL(h.t, r.dy)) : 0.0f;
-        point_out[3 * i + 2] = hit ? XADD(r.oz, XMUL(h.t, r.dz)) : 0.0f;
-    }
+    PathStats st = {0, 0, 0};
+    const long long n_lanes = 5;
+    for (long long l = 0; l < n_lanes; ++l) { BatchPolicy pol(org, dir, n, l, n_lanes, tri_out, dist_out, point_out, st); run_lane<true>(s->view, pol, &cn); }
     if (counters4) { counters4[0] = cn.branch_visits; counters4[1] = cn.child_box_tests; counters4[2] = cn.tri_tests; counters4[3] = cn.rays; }
 }
 
-// One render, all lanes run one after the other.  stats5 = rays, samples, primary_reused, branch_visits, tri_tests
+// One render.  The device runs 32 lanes per warp in lock step; lanes are independent, so here `n_lanes` software
+// lanes each run to completion, sharing one work queue like the device lanes share the atomic counter.
+// stats5 = rays, samples, primary_reused, branch_visits, tri_tests
 void emu_render(emu_scene *s, const sqt_camera *cam, const sqt_render_params *p, int rank, int world, float *accum,
                 unsigned char *rgb8, unsigned long long *stats5) {
     RenderParams d = {};
@@ -74,24 +70,24 @@ void emu_render(emu_scene *s, const sqt_camera *cam, const sqt_render_params *p,
     std::memset(accum, 0, (size_t)npix * 12);
     Counters cn = {0, 0, 0, 0};
     PathStats st = {0, 0, 0};
+    const long long n_lanes = 7;
     if (d.mode == 1) {
-        for (long long w = 0; w < nwork; ++w) { const long long pix = work_to_pixel(d, w); if (pix >= 0) raycast_pixel<true>(s->view, d, pix, accum, &cn, st); }
+        for (long long l = 0; l < n_lanes; ++l) { CastPolicy pol(d, accum, nwork, l, n_lanes, st); run_lane<true>(s->view, pol, &cn); }
     } else {
         std::vector<int2> prim;
         if (d.primary_reuse) {
             prim.resize((size_t)npix);
-            for (long long w = 0; w < nwork; ++w) {
-                const long long pix = work_to_pixel(d, w);
-                if (pix < 0) continue;
-                const Ray r = make_ray(d, (int)(pix / d.cols), (int)(pix % d.cols));
-                const Hit h = traverse<true>(s->view, r, &cn);
-                st.rays += 1;
-                prim[(size_t)pix].x = h.tri; prim[(size_t)pix].y = (int)f2u(h.t);
-            }
+            for (long long l = 0; l < n_lanes; ++l) { PrimaryPolicy pol(d, prim.data(), nwork, l, n_lanes, st); run_lane<true>(s->view, pol, &cn); }
         }
-        // emulate 7 interleaved "lanes" pulling from one queue, to exercise the dynamic fetch order independence
         SeqFetch fetch{0, nwork};
-        render_lane<true>(s->view, d, d.primary_reuse ? prim.data() : nullptr, accum, fetch, &cn, st);
+        uint16_t pm[SQT_MAX_DEPTH];
+        for (long long l = 0; l < n_lanes; ++l) {
+            // each lane drains what is left of the queue after taking a few items, like lanes racing on the counter
+            SeqFetch part{fetch.next, l + 1 == n_lanes ? nwork : std::min(nwork, fetch.next + (nwork + n_lanes - 1) / n_lanes)};
+            PathPolicy<SeqFetch> pol(d, d.primary_reuse ? prim.data() : nullptr, accum, part, st, pm);
+            run_lane<true>(s->view, pol, &cn);
+            fetch.next = part.n;
+        }
     }
     if (rgb8) {
         const float inv = 1.0f / (float)d.spp;

@@ -1,0 +1,244 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (include/sqt.h), against the CPU oracle.
+
+Bar: bit-exact for hit index, dist, hit point, the float accumulation buffer and the RGB8 image (integer/byte/
+index work and -- because the oracle restates the device's "sqt trig" polynomials and shares the counter-based
+RNG -- the floating-point image too).  Against the reference-faithful libm oracle the bar is a stated RMSE.
+"""
+import numpy as np
+import pytest
+
+import pysqt
+from oracle import oracle as O
+from pysqt import scenes
+
+from common import adversarial_rays, assert_same_hits, bits, build_pair, random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_is_b200(gpu_ctx):
+    info = gpu_ctx.info()
+    assert info["cc"][0] == 10, info
+    assert info["sm_count"] >= 100
+
+
+# ------------------------------------------------------------------ closest hit, bit exact
+def test_primary_rays_bit_exact(gpu_ctx, host_scene, oracle_scene, camera):
+    gpu_ctx.upload(host_scene)
+    org, dirs = O.make_rays(O.make_params(540, 540, 1), camera)
+    got = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
+    want = oracle_scene.intersect_batch(org, dirs, counters=True)
+    assert_same_hits(got, want, "primary 540x540")
+    st, cn = got[3], want[3]
+    # the traversal visits exactly the reference's subtrees: same branch visits and triangle tests
+    assert st["branch_visits"] == int(cn[0]) and st["child_box_tests"] == int(cn[1]) and st["tri_tests"] == int(cn[3])
+    assert st["rays_traced"] == len(org)
+
+
+def test_literal_nonsquare_primary_rays(gpu_ctx, host_scene, oracle_scene, camera):
+    gpu_ctx.upload(host_scene)
+    org, dirs = O.make_rays(O.make_params(320, 200, 1, literal=True), camera)
+    assert_same_hits(gpu_ctx.intersect_batch(org, dirs), oracle_scene.intersect_batch(org, dirs), "literal 320,200")
+
+
+def test_random_incoherent_rays_bit_exact(gpu_ctx, host_scene, oracle_scene):
+    gpu_ctx.upload(host_scene)
+    org, dirs = random_rays(300_000, seed=11)
+    assert_same_hits(gpu_ctx.intersect_batch(org, dirs), oracle_scene.intersect_batch(org, dirs), "random")
+
+
+def test_adversarial_rays_bit_exact(gpu_ctx, host_scene, oracle_scene):
+    gpu_ctx.upload(host_scene)
+    v9, _ = oracle_scene.tris()
+    org, dirs = adversarial_rays(v9)
+    assert_same_hits(gpu_ctx.intersect_batch(org, dirs), oracle_scene.intersect_batch(org, dirs), "adversarial")
+
+
+def test_matches_naive_intersect_up_to_ties(gpu_ctx, host_scene, oracle_scene, camera):
+    """The reference's own differential pair (naiveIntersect vs intersectBIH): same dist always, same triangle
+    except exact ties."""
+    gpu_ctx.upload(host_scene)
+    org, dirs = O.make_rays(O.make_params(96, 96, 1), camera)
+    tri, dist, _ = gpu_ctx.intersect_batch(org, dirs)
+    ntri, ndist, _ = oracle_scene.intersect_batch(org, dirs, naive=True)
+    assert np.array_equal((tri >= 0), (ntri >= 0))
+    assert np.array_equal(bits(dist), bits(ndist))
+    assert (tri != ntri).mean() < 0.01
+
+
+def test_recorded_bounce_rays(gpu_ctx, host_scene, oracle_scene, camera):
+    """Secondary rays: origins on surfaces (self-hit rejection by t > eps), unit scatter directions."""
+    gpu_ctx.upload(host_scene)
+    org, dirs = O.make_rays(O.make_params(200, 200, 1), camera)
+    tri, dist, point = oracle_scene.intersect_batch(org, dirs)
+    hit = tri >= 0
+    rng = np.random.default_rng(3)
+    d2 = rng.normal(size=(hit.sum(), 3)).astype(np.float32)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True).astype(np.float32)
+    assert_same_hits(gpu_ctx.intersect_batch(point[hit], d2), oracle_scene.intersect_batch(point[hit], d2), "bounce")
+
+
+def test_empty_batch_and_errors(gpu_ctx, host_scene):
+    gpu_ctx.upload(host_scene)
+    tri, dist, point = gpu_ctx.intersect_batch(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert len(tri) == 0
+    fresh = pysqt.Context(0)
+    with pytest.raises(pysqt.SqtError, match="before sqt_upload_scene"):
+        fresh.intersect_batch(np.zeros((1, 3), np.float32), np.ones((1, 3), np.float32))
+    bad = host_scene.desc()
+    bad.n_mats = 0
+    assert fresh.upload_desc_raw(bad) == 1 and "materials" in fresh.last_error()
+    p = pysqt.make_params(8, 8, 1, max_depth=0)
+    fresh.upload(host_scene)
+    with pytest.raises(pysqt.SqtError, match="max_depth"):
+        fresh.render(pysqt.load_camera(pysqt.ROOT + "/data/camera"), p)
+    fresh.close()
+
+
+@pytest.mark.parametrize("n_tris", [1, 9, 14])
+def test_root_leaf_scene(gpu_ctx, n_tris):
+    """Fewer than 15 triangles: the tree is a single Leaf and no box test happens at all (BIH.hs:69,105)."""
+    v9, mi, mats = scenes.triangle_soup(n_tris, seed=2)
+    osc, hs = build_pair(v9 * 40.0, mi, mats)
+    assert hs.n_nodes == 1
+    gpu_ctx.upload(hs)
+    org, dirs = random_rays(20000, seed=4, lo=-1, hi=1)
+    assert_same_hits(gpu_ctx.intersect_batch(org, dirs), osc.intersect_batch(org, dirs), "root leaf")
+
+
+def test_degenerate_split_and_empty_leaves(gpu_ctx):
+    """All centroids equal on the split axis -> one side empty -> Branch (Leaf empty) (Leaf everything), a leaf
+    longer than 14 (BIH.hs:70-75)."""
+    rng = np.random.default_rng(8)
+    n = 40
+    base = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32) * np.array([0, 1, 1], np.float32)   # x centroid identical
+    offs = np.array([[0.3, 0, 0], [-0.15, 0.2, 0.1], [-0.15, -0.2, -0.1]], np.float32)
+    v9 = (base * np.array([1e-3, 1e-3, 1e-3], np.float32) + offs[None]).reshape(n, 9)
+    mats = np.array([[0, .5, .5, .5, 0, 0, 0, 0]], np.float32)
+    osc, hs = build_pair(v9, np.zeros(n, np.int32), mats)
+    assert hs.stats()["longest_leaf"] > 14
+    gpu_ctx.upload(hs)
+    org, dirs = random_rays(20000, seed=5, lo=-1, hi=1)
+    assert_same_hits(gpu_ctx.intersect_batch(org, dirs), osc.intersect_batch(org, dirs), "degenerate")
+
+
+@pytest.mark.parametrize("gen,n", [("cornell", 10000), ("soup", 60000), ("mesh", 80000)])
+def test_synthetic_scenes_bit_exact(gpu_ctx, gen, n):
+    v9, mi, mats = {"cornell": scenes.cornell_box, "soup": scenes.triangle_soup, "mesh": scenes.subdivided_mesh}[gen](n)
+    osc, hs = build_pair(v9, mi, mats)
+    gpu_ctx.upload(hs)
+    org, dirs = random_rays(100_000, seed=21, lo=-1.5, hi=1.5)
+    got = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
+    want = osc.intersect_batch(org, dirs, counters=True)
+    assert_same_hits(got, want, gen)
+    assert got[3]["tri_tests"] == int(want[3][3]) and got[3]["branch_visits"] == int(want[3][0])
+
+
+# ------------------------------------------------------------------ rendered image
+@pytest.mark.parametrize("w,h,spp,depth,literal", [(96, 64, 8, 3, False), (64, 64, 6, 8, False), (80, 48, 5, 3, True), (48, 48, 3, 1, False)])
+def test_render_bit_exact_vs_oracle(gpu_ctx, host_scene, oracle_scene, camera, w, h, spp, depth, literal):
+    gpu_ctx.upload(host_scene)
+    out = gpu_ctx.render(camera, pysqt.make_params(w, h, spp, max_depth=depth, seed=5, literal=literal))
+    ref = oracle_scene.render(camera, O.make_params(w, h, spp, max_depth=depth, seed=5, trig=1, literal=literal))
+    assert out["accum"].shape == ref["accum"].shape
+    assert np.array_equal(bits(out["accum"]), bits(ref["accum"]))
+    assert np.array_equal(out["rgb8"], ref["rgb8"])
+    assert out["stats"]["samples"] == ref["samples"] == w * h * spp
+    assert out["stats"]["rays_traced"] <= ref["rays"]
+
+
+def test_render_reference_work_flags_match_oracle_counts(gpu_ctx, host_scene, oracle_scene, camera):
+    """With primary reuse and early termination off the device traces exactly the reference's rays: ray count,
+    branch visits and triangle tests equal the oracle's counters."""
+    gpu_ctx.upload(host_scene)
+    f = pysqt.SQT_F_NO_PRIMARY_REUSE | pysqt.SQT_F_NO_EARLY_TERMINATION | pysqt.SQT_F_COUNT_WORK
+    out = gpu_ctx.render(camera, pysqt.make_params(72, 56, 6, max_depth=4, seed=9, flags=f))
+    ref = oracle_scene.render(camera, O.make_params(72, 56, 6, max_depth=4, seed=9, trig=1))
+    assert np.array_equal(bits(out["accum"]), bits(ref["accum"]))
+    st, cn = out["stats"], ref["counters"]
+    assert st["rays_traced"] == ref["rays"]
+    assert st["branch_visits"] == cn["branch_visits"] and st["tri_tests"] == cn["tri_tests"]
+    assert st["child_box_tests"] == cn["child_box_tests"]
+
+
+def test_render_rmse_vs_reference_faithful_libm_oracle(gpu_ctx, host_scene, oracle_scene, camera):
+    """Against the oracle in libm mode (cosf/sinf/acosf/atanf as GHC calls them): stated tolerance
+    per-pixel RMSE of the mean radiance <= 2e-3 (scene radiance scale: light = 100), RGB8 may differ by 1 level
+    on < 0.1% of the bytes."""
+    gpu_ctx.upload(host_scene)
+    w, h, spp = 128, 128, 64
+    out = gpu_ctx.render(camera, pysqt.make_params(w, h, spp, max_depth=3, seed=1))
+    ref = oracle_scene.render(camera, O.make_params(w, h, spp, max_depth=3, seed=1, trig=0))
+    rmse = float(np.sqrt(np.mean((out["accum"] / spp - ref["accum"] / spp) ** 2)))
+    assert rmse <= 2e-3, rmse
+    d = np.abs(out["rgb8"].astype(int) - ref["rgb8"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+def test_cast_mode_bit_exact(gpu_ctx, host_scene, oracle_scene, camera):
+    gpu_ctx.upload(host_scene)
+    out = gpu_ctx.render(camera, pysqt.make_params(120, 90, 4, mode=1))
+    ref = oracle_scene.render(camera, O.make_params(120, 90, 4, mode=1, trig=1))
+    assert np.array_equal(bits(out["accum"]), bits(ref["accum"]))
+    assert np.array_equal(out["rgb8"], ref["rgb8"])
+
+
+def test_tone_map_bit_exact(gpu_ctx):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(0, 3, (5000, 3)), rng.uniform(0, 200, (2000, 3)), np.zeros((4, 3)),
+                        np.array([[0, 0, 1e-30], [1e20, 1, 0], [np.inf, 1, 1], [0.4142135, 0.4142136, 2.4142137]])]).astype(np.float32)
+    assert np.array_equal(gpu_ctx.tone_map(x), O.tone_map(x, 1, trig=1))
+
+
+def test_resident_then_download_equals_render(gpu_ctx, host_scene, camera):
+    gpu_ctx.upload(host_scene)
+    p = pysqt.make_params(64, 48, 4, max_depth=3, seed=2)
+    a = gpu_ctx.render(camera, p)
+    st = gpu_ctx.render_resident(camera, p)
+    rgb8, accum = gpu_ctx.download(p.rows, p.cols)
+    assert np.array_equal(a["rgb8"], rgb8) and np.array_equal(bits(a["accum"]), bits(accum))
+    assert st["rays_traced"] == a["stats"]["rays_traced"] and st["kernel_launches"] == 3
+
+
+def test_render_is_deterministic_and_seed_sensitive(gpu_ctx, host_scene, camera):
+    gpu_ctx.upload(host_scene)
+    p = pysqt.make_params(64, 64, 16, max_depth=4, seed=11)
+    a = gpu_ctx.render(camera, p)["accum"]
+    b = gpu_ctx.render(camera, p)["accum"]
+    c = gpu_ctx.render(camera, pysqt.make_params(64, 64, 16, max_depth=4, seed=12))["accum"]
+    assert np.array_equal(bits(a), bits(b))
+    assert not np.array_equal(a, c)
+
+
+def test_synthetic_cornell_render_bit_exact(gpu_ctx, camera):
+    v9, mi, mats = scenes.cornell_box(10000)
+    osc, hs = build_pair(v9, mi, mats)
+    gpu_ctx.upload(hs)
+    out = gpu_ctx.render(camera, pysqt.make_params(64, 48, 4, max_depth=6, seed=4))
+    ref = osc.render(camera, O.make_params(64, 48, 4, max_depth=6, seed=4, trig=1))
+    assert np.array_equal(bits(out["accum"]), bits(ref["accum"]))
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties
+def test_full_size_properties_1080p(gpu_ctx, host_scene, oracle_scene, camera):
+    """BASELINE config 2 geometry (1920x1080, depth 8) at a reduced spp the oracle cannot follow in full:
+    (1) a random sample of pixels is re-rendered by the oracle and must match bit for bit,
+    (2) pixels whose primary ray misses are exactly black, (3) sample accounting is exact,
+    (4) a second run is bit-identical (dynamic work fetch does not leak into the result)."""
+    gpu_ctx.upload(host_scene)
+    W, H, spp, depth = 1920, 1080, 16, 8
+    p = pysqt.make_params(W, H, spp, max_depth=depth, seed=77)
+    out = gpu_ctx.render(camera, p)
+    acc = out["accum"]
+    assert out["stats"]["samples"] == W * H * spp
+    org, dirs = O.make_rays(O.make_params(W, H, 1), camera)
+    tri, _, _ = gpu_ctx.intersect_batch(org, dirs)
+    miss = (tri < 0).reshape(H, W)
+    assert np.all(acc[miss] == 0)
+    rng = np.random.default_rng(0)
+    op = O.make_params(W, H, spp, max_depth=depth, seed=77, trig=1)
+    for r in np.sort(rng.choice(H, 6, replace=False)):
+        row = O.render_window(oracle_scene, camera, op, int(r) * W, (int(r) + 1) * W)
+        assert np.array_equal(bits(acc[r]), bits(row)), "row %d differs" % r
+    again = gpu_ctx.render(camera, p)["accum"]
+    assert np.array_equal(bits(acc), bits(again))
