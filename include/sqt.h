@@ -114,6 +114,7 @@ typedef struct sqt_stats {
     uint64_t rays_reference;     /* queries the reference would execute for the same job (Lib.hs:131 per segment) */
     uint64_t samples;            /* paths (Lib.hs:84) */
     uint64_t branch_visits, child_box_tests, tri_tests;    /* only with SQT_F_COUNT_WORK */
+    uint64_t leaves_culled;      /* leaf visits skipped by the conservative tight-box test (with SQT_F_COUNT_WORK) */
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t kernel_launches;
     uint32_t reserved;
@@ -165,6 +166,11 @@ int sqt_render_group(sqt_ctx **ctxs, int n, const sqt_camera *cam, const sqt_ren
 /* measured roofline denominators on this device (microbenchmarks) ------------- */
 int sqt_measure_fp32_peak(sqt_ctx *ctx, double *gops_per_s);     /* non-fused FADD/FMUL issue rate, Gop/s */
 int sqt_measure_l2_bandwidth(sqt_ctx *ctx, double *gb_per_s);    /* L2-resident 128-bit read bandwidth */
+
+/* options: SQT_OPT_LEAF_CULL (default 1) -- skip leaves whose conservatively enlarged tight box the ray
+ * misses.  Exact; 0 reproduces the reference's triangle-test count one for one. */
+#define SQT_OPT_LEAF_CULL 1
+int sqt_set_option(sqt_ctx *ctx, int option, int value);
 
 /* introspection used by tests */
 int sqt_device_info(sqt_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, char name_out[128]);

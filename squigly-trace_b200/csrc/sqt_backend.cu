@@ -31,9 +31,8 @@ using namespace sqt;
 // =============================================================================== kernels
 struct DeviceStats {
     unsigned long long rays, samples, primary_reused;
-    unsigned long long branch_visits, child_box_tests, tri_tests;
+    unsigned long long branch_visits, child_box_tests, tri_tests, leaves_culled;
     unsigned long long work_next;       // dynamic work counter of k_paths
-    unsigned long long pad;
 };
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -44,52 +43,67 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 __device__ __forceinline__ void flush_stats(DeviceStats *ds, const PathStats &st, const Counters &cn, bool count) {
     unsigned long long r = warp_sum(st.rays), s = warp_sum(st.samples), p = warp_sum(st.primary_reused);
     unsigned long long b = 0, c = 0, t = 0;
-    if (count) { b = warp_sum(cn.branch_visits); c = warp_sum(cn.child_box_tests); t = warp_sum(cn.tri_tests); }
+    unsigned long long lc = 0;
+    if (count) { b = warp_sum(cn.branch_visits); c = warp_sum(cn.child_box_tests); t = warp_sum(cn.tri_tests); lc = warp_sum(cn.leaves_culled); }
     if ((threadIdx.x & 31) == 0) {
         if (r) atomicAdd(&ds->rays, r);
         if (s) atomicAdd(&ds->samples, s);
         if (p) atomicAdd(&ds->primary_reused, p);
-        if (count) { atomicAdd(&ds->branch_visits, b); atomicAdd(&ds->child_box_tests, c); atomicAdd(&ds->tri_tests, t); }
+        if (count) { atomicAdd(&ds->branch_visits, b); atomicAdd(&ds->child_box_tests, c); atomicAdd(&ds->tri_tests, t); atomicAdd(&ds->leaves_culled, lc); }
     }
 }
 
-// Scheduling knobs of the warp-synchronous loop (runtime so that they can be tuned without rebuilding):
+// Scheduling knobs of the warp-synchronous loop (runtime so that they can be tuned without rebuilding; they
+// change the order in which lanes get served, never a result):
 //   a_leave : leave the traversal phase once at most this many lanes still want a traversal step
 //   b_leave : leave the triangle phase once fewer than this many lanes still have triangles to test
 //   c_min   : run the regeneration phase only when at least this many lanes are done (or nothing else can run)
 struct Tune { int a_leave, b_leave, c_min; };
 
-// The persistent warp loop.  Every lane of the warp stays in it until all 32 have run out of work; the phase
-// boundaries are warp votes, so divergent lanes are forced back together three times per round instead of
-// drifting apart through the data-dependent traversal (which is what an ordinary per-lane loop nest compiles to).
+// The persistent warp loop.  Every lane of the warp stays in it until all 32 have run out of work.  A round is
+// three phases, each a tight loop whose trip count is decided by a warp vote: regeneration (consume the finished
+// hit, shade, make the next ray), traversal steps (stack pops + one branch visit), triangle steps (one
+// Moller-Trumbore test).  The votes force the 32 lanes back together at every phase boundary; an ordinary
+// per-lane loop nest compiles to code where the lanes drift apart through the data-dependent traversal and
+// never reconverge (measured: 2.4 of 32 lanes active, profiles/r01_k_paths_v0_divergent.txt).
 template <bool COUNT, class Policy>
 __device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Counters *cn, const Tune tn) {
     const unsigned FULL = 0xffffffffu;
     uint32_t stack[kStackWords];
     TravLane L;
     L.stack = stack;
-    L.state = ST_DONE; L.sp = 0; L.i = 0; L.child = 0u; L.meta = 0u; L.safe = true;
+    L.state = ST_DONE; L.sp = 0; L.i = 0; L.child = 0u; L.meta = 0u; L.safe = true; L.sgn = 0u; L.dfac = 0.0f;
     L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
     L.dfx = L.dfy = L.dfz = 0.0f;
     L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
     for (;;) {
-        // ---- regeneration: lanes whose ray finished consume the hit and produce their next ray
+        // ---- regeneration
         const unsigned m_done = __ballot_sync(FULL, L.state == ST_DONE);
-        const unsigned m_busy = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET || L.state == ST_LEAF);
+        const unsigned m_busy = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET || L.state == ST_LEAF || L.state == ST_ENTER);
         if (m_done != 0u && (__popc(m_done) >= tn.c_min || m_busy == 0u)) {
             if (L.state == ST_DONE) pol.template regen<COUNT>(sc, L, cn);
             __syncwarp(FULL);
         } else if (m_busy == 0u) break;                       // every lane is ST_EXIT
-        // ---- traversal steps (branch visits, stack pops)
-        unsigned m = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET);
-        while (m != 0u) {
-            if (L.state == ST_RET) ret_step(sc, L);
-            if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
-            m = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET);
-            if (__popc(m) <= tn.a_leave) break;
+        // ---- traversal steps (stack pops + one branch visit) while more than a_leave lanes want one; then every
+        //      lane that found a leaf enters it (record fetch + conservative culling; culled lanes traverse on).
+        //      The few stragglers left over keep their state and continue next round.
+        for (;;) {
+            const unsigned mt = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET);
+            const unsigned me = __ballot_sync(FULL, L.state == ST_ENTER);
+            const unsigned ml = __ballot_sync(FULL, L.state == ST_LEAF);
+            if (__popc(mt) > tn.a_leave || (mt != 0u && (me | ml) == 0u)) {
+                if (L.state == ST_RET) ret_step(sc, L);
+                if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
+                continue;
+            }
+            if (me != 0u) {
+                if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, cn);
+                continue;
+            }
+            break;
         }
-        // ---- triangle steps (one Moller-Trumbore test per lane per iteration)
-        m = __ballot_sync(FULL, L.state == ST_LEAF);
+        // ---- triangle steps
+        unsigned m = __ballot_sync(FULL, L.state == ST_LEAF);
         while (m != 0u) {
             if (L.state == ST_LEAF) tri_step(sc, L);
             m = __ballot_sync(FULL, L.state == ST_LEAF);
@@ -103,7 +117,7 @@ __global__ void __launch_bounds__(128) k_intersect_batch(SceneView sc, const flo
                                                          const float *__restrict__ dir, long long n,
                                                          int *__restrict__ tri_out, float *__restrict__ dist_out,
                                                          float *__restrict__ point_out, DeviceStats *ds, Tune tn) {
-    Counters cn = {0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0};
     PathStats st = {0, 0, 0};
     BatchPolicy pol(org, dir, n, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, tri_out,
                     dist_out, point_out, st);
@@ -113,7 +127,7 @@ __global__ void __launch_bounds__(128) k_intersect_batch(SceneView sc, const flo
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_primary(SceneView sc, RenderParams p, int2 *__restrict__ prim, DeviceStats *ds, Tune tn) {
-    Counters cn = {0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0};
     PathStats st = {0, 0, 0};
     PrimaryPolicy pol(p, prim, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, st);
     warp_loop<COUNT>(sc, pol, &cn, tn);
@@ -137,7 +151,7 @@ struct DeviceFetch {
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, const int2 *__restrict__ prim,
                                                float *__restrict__ accum, DeviceStats *ds, Tune tn) {
-    Counters cn = {0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0};
     PathStats st = {0, 0, 0};
     DeviceFetch fetch = {&ds->work_next, work_items(p)};
     uint16_t pm[SQT_MAX_DEPTH];
@@ -148,7 +162,7 @@ __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, con
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_raycast(SceneView sc, RenderParams p, float *__restrict__ accum, DeviceStats *ds, Tune tn) {
-    Counters cn = {0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0};
     PathStats st = {0, 0, 0};
     CastPolicy pol(p, accum, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, st);
     warp_loop<COUNT>(sc, pol, &cn, tn);
@@ -239,7 +253,8 @@ struct sqt_ctx {
     // scene
     bool has_scene = false;
     SceneView sc = {};
-    float4 *d_nodes = nullptr, *d_tris = nullptr, *d_mats = nullptr;
+    float4 *d_nodes = nullptr, *d_tris = nullptr, *d_mats = nullptr, *d_leaves = nullptr;
+    int leaf_cull = 1;
     int terminate_on_black_ok = 0;
     uint32_t tree_height = 0;
     // image buffers
@@ -257,7 +272,7 @@ struct sqt_ctx {
     int *d_tri = nullptr;
     // pinned host staging for image I/O
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
-    Tune tune = {0, 1, 1};
+    Tune tune = {8, 1, 4};
     // group
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -309,8 +324,8 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
 }
 
 static void free_scene(sqt_ctx *c) {
-    cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_mats);
-    c->d_nodes = c->d_tris = c->d_mats = nullptr; c->has_scene = false;
+    cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_mats); cudaFree(c->d_leaves);
+    c->d_nodes = c->d_tris = c->d_mats = c->d_leaves = nullptr; c->has_scene = false;
 }
 
 extern "C" int sqt_destroy(sqt_ctx *c) {
@@ -356,17 +371,26 @@ extern "C" int sqt_upload_scene(sqt_ctx *ctx, const sqt_scene_desc *s) {
     CU(cudaMalloc(&ctx->d_nodes, dn.size() * sizeof(float4)));
     CU(cudaMalloc(&ctx->d_tris, (size_t)(s->n_tris ? s->n_tris : 1) * 48));
     CU(cudaMalloc(&ctx->d_mats, dm.size() * sizeof(float4)));
+    CU(cudaMalloc(&ctx->d_leaves, lay.leaves.size() * sizeof(float4)));
+    CU(cudaMemcpyAsync(ctx->d_leaves, lay.leaves.data(), lay.leaves.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_nodes, dn.data(), dn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     if (s->n_tris) CU(cudaMemcpyAsync(ctx->d_tris, s->tris, (size_t)s->n_tris * 48, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_mats, dm.data(), dm.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     SceneView v = {};
-    v.nodes = ctx->d_nodes; v.tris = ctx->d_tris; v.mats = ctx->d_mats;
+    v.nodes = ctx->d_nodes; v.tris = ctx->d_tris; v.mats = ctx->d_mats; v.leaves = ctx->d_leaves;
+    v.leaf_cull = (uint32_t)ctx->leaf_cull;
     for (int k = 0; k < 3; ++k) { v.root_lo[k] = s->root_bounds[k]; v.root_hi[k] = s->root_bounds[3 + k]; }
     v.n_branches = n_br; v.n_tris = s->n_tris; v.n_mats = s->n_mats;
     v.root_is_leaf = (s->nodes[0].b & SQT_NODE_LEAF) ? 1u : 0u;
     ctx->sc = v; ctx->has_scene = true; ctx->terminate_on_black_ok = tob; ctx->tree_height = height;
     return SQT_OK;
+}
+
+extern "C" int sqt_set_option(sqt_ctx *ctx, int option, int value) {
+    if (!ctx) return SQT_E_INVALID;
+    if (option == SQT_OPT_LEAF_CULL) { ctx->leaf_cull = value ? 1 : 0; ctx->sc.leaf_cull = (uint32_t)ctx->leaf_cull; return SQT_OK; }
+    return fail(ctx, SQT_E_INVALID, "unknown option %d", option);
 }
 
 // ------------------------------------------------------------------------------ helpers
@@ -446,7 +470,7 @@ extern "C" int sqt_intersect_batch(sqt_ctx *ctx, const float *org, const float *
         stats->d2h_ms = ev_ms(ctx->ev[2], ctx->ev[3]);
         stats->rays_traced = ctx->h_stats->rays; stats->rays_reference = ctx->h_stats->rays;
         stats->branch_visits = ctx->h_stats->branch_visits; stats->child_box_tests = ctx->h_stats->child_box_tests;
-        stats->tri_tests = ctx->h_stats->tri_tests;
+        stats->tri_tests = ctx->h_stats->tri_tests; stats->leaves_culled = ctx->h_stats->leaves_culled;
         stats->h2d_bytes = (uint64_t)n * 24; stats->d2h_bytes = (uint64_t)n * (4 + (dist_out ? 4 : 0) + (point_out ? 12 : 0));
         stats->kernel_launches = 1;
     }
@@ -534,7 +558,7 @@ static void fill_stats(sqt_ctx *ctx, sqt_stats *s, uint32_t launches) {
     s->rays_traced = ctx->h_stats->rays; s->samples = ctx->h_stats->samples;
     s->rays_reference = ctx->h_stats->rays + ctx->h_stats->primary_reused;
     s->branch_visits = ctx->h_stats->branch_visits; s->child_box_tests = ctx->h_stats->child_box_tests;
-    s->tri_tests = ctx->h_stats->tri_tests;
+    s->tri_tests = ctx->h_stats->tri_tests; s->leaves_culled = ctx->h_stats->leaves_culled;
     s->kernel_launches = launches;
 }
 

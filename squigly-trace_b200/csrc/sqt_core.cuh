@@ -50,35 +50,48 @@ struct alignas(8) int2 { int x, y; };
 namespace sqt {
 
 // ---------------------------------------------------------------------------- device records
-// Branch node, 48 B = 3 x 128-bit loads.  The box is the node's own clipped box, i.e. the `bbox`
-// argument intersectBIH' receives for this node (BIH.hs:111,130-141) -- a static property of the
-// tree, derived at upload time by copying planes (no arithmetic).
-//   q0 = (lo.x, lo.y, lo.z, hi.x)   q1 = (hi.y, hi.z, lmax, rmin)
-//   q2 = (left, right, lmeta, rmeta) as u32 bits:
+// Branch node, 64 B = 4 x 128-bit loads.  `lo`/`hi` are the node's own clipped box, i.e. the `bbox`
+// argument intersectBIH' receives for this node (BIH.hs:111,130-141); Lhi = hi with hi[axis] := lmax is
+// the upper corner of the left child's box, Rlo = lo with lo[axis] := rmin the lower corner of the right
+// child's box.  All are static properties of the tree, derived at upload time by copying planes (no
+// arithmetic).  Storing both corners makes the two child slab tests axis-free (no per-lane selects).
+//   q0 = (lo.x, lo.y, lo.z, hi.x)   q1 = (hi.y, hi.z, Lhi.x, Lhi.y)   q2 = (Lhi.z, Rlo.x, Rlo.y, Rlo.z)
+//   q3 = (left, right, lmeta, rmeta) as u32 bits:
 //        child is Branch: ref = index into the branch array, meta = 0
-//        child is Leaf  : ref = first triangle,             meta = LEAF | count
-//        lmeta additionally carries the split axis in bits 28..29
+//        child is Leaf  : ref = index into the leaf array,   meta = kLeaf | count
+// Leaf record, 32 B = 2 x 128-bit loads: the TIGHT bounding box of the leaf's triangles and their longest
+// edge, used only by the conservative leaf culling below (never by the reference algorithm):
+//   b0 = (lo.x, lo.y, lo.z, hi.x)   b1 = (hi.y, hi.z, longest edge E, first triangle as u32 bits)
+//        lmeta additionally carries the split axis in bits 27..28
+// Traversal stack entries are 3 words:
+//   phase A (near subtree in flight): { isClose plane (rmin if left-to-right else lmax), far child ref,
+//                                       far meta | axis << 27 | kLtr if left-to-right }
+//   phase B (near hit parked, far subtree in flight): { t bits, dist bits, tri | kPhaseB }
 constexpr uint32_t kLeaf = 0x80000000u;
-constexpr uint32_t kAxisShift = 28;
-constexpr uint32_t kCountMask = 0x0fffffffu;
-constexpr uint32_t kPhaseB = 0x80000000u;
-constexpr int kStackWords = 3 * 48 + 4;
+constexpr uint32_t kPhaseB = 0x40000000u;
+constexpr uint32_t kLtr = 0x20000000u;
+constexpr uint32_t kAxisShift = 27;
+constexpr uint32_t kCountMask = 0x07ffffffu;
+constexpr int kNodeQuads = 4;
+constexpr int kStackWords = 3 * 48;            // one 3-word entry per tree level at most
 #ifndef SQT_MAX_DEPTH
 #define SQT_MAX_DEPTH 64
-#endif        // worst case: every frame parked in phase B (3 words)
+#endif
 
 struct SceneView {
-    const float4 *nodes;     // 3 float4 per branch
+    const float4 *nodes;     // kNodeQuads float4 per branch
+    const float4 *leaves;    // 2 float4 per leaf
     const float4 *tris;      // 3 float4 per triangle: (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z, mat, orig, pad)
     const float4 *mats;      // 3 float4 per material: (refl, surf.rgb) (emissive, emit.rgb) (ec.rgb, flags)
     float root_lo[3], root_hi[3];
     uint32_t n_branches, n_tris, n_mats;
     uint32_t root_is_leaf;   // tree = Leaf: no box test at all (BIH.hs:105)
+    uint32_t leaf_cull;      // 1 = skip leaves whose enlarged tight box the ray provably misses (exact, see enter_leaf)
 };
 
 struct Ray { float ox, oy, oz, dx, dy, dz; };
 struct Hit { int tri; float t; float dist; };      // tri = index in leaf order, -1 = Nothing
-struct Counters { unsigned long long branch_visits, child_box_tests, tri_tests, rays; };
+struct Counters { unsigned long long branch_visits, child_box_tests, tri_tests, rays, leaves_culled; };
 
 SQT_HD uint32_t f2u(float f) {
 #if defined(__CUDA_ARCH__)
@@ -100,7 +113,6 @@ SQT_HD float hs_max(float x, float y) { return (x <= y) ? y : x; }
 SQT_HD float hs_min(float x, float y) { return (x <= y) ? x : y; }
 // compare a b == GT  (anything against NaN is GT)
 SQT_HD bool cmp_gt(float a, float b) { return !(a < b) && !(a == b); }
-SQT_HD float sel3(int ax, float x, float y, float z) { return ax == 0 ? x : (ax == 1 ? y : z); }
 SQT_HD bool finite_f(float x) { return fabsf(x) < INFINITY; }   // false for inf and NaN
 
 // V3.hs:25-26  dot = (a*d)+(b*e)+(c*f)
@@ -120,34 +132,39 @@ SQT_HD bool slab_exact(float lx, float ly, float lz, float hx, float hy, float h
     return tmax > 0.0f && tmin < tmax;
 }
 
-// Both child boxes of a branch (BIH.hs:128-141).  `safe` rays (all 1/dir finite, origin not NaN)
-// cannot produce a NaN slab value, and without NaNs min/max are exact, order-free operations whose
-// zero sign never reaches the two comparisons -- so the hardware FMNMX path is used and the planes
-// shared by both children are evaluated once.  Unsafe rays take the literal path.
-SQT_HD void slab_children(const float4 &q0, const float4 &q1, int ax, const Ray &r, float dfx, float dfy,
+// branch-free 3-way select (the compiler turns the ?: chain into divergent branches otherwise)
+SQT_HD float sel3(int ax, float x, float y, float z) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("{\n\t.reg .pred p1, p2;\n\tsetp.eq.s32 p1, %4, 1;\n\tsetp.eq.s32 p2, %4, 2;\n\t"
+        "selp.f32 %0, %2, %1, p1;\n\tselp.f32 %0, %3, %0, p2;\n\t}"
+        : "=&f"(r) : "f"(x), "f"(y), "f"(z), "r"(ax));
+    return r;
+#else
+    return ax == 0 ? x : (ax == 1 ? y : z);
+#endif
+}
+
+// Both child boxes of a branch (BIH.hs:128-141): left = (lo, Lhi), right = (Rlo, hi).  `safe` rays (all
+// 1/dir finite, origin finite) cannot produce a NaN slab value, and without NaNs min/max are exact,
+// order-free operations whose zero sign never reaches the two comparisons -- so the hardware FMNMX path is
+// used.  Unsafe rays take the literal Geometry.hs:166-177 path.
+SQT_HD void slab_children(const float4 &q0, const float4 &q1, const float4 &q2, const Ray &r, float dfx, float dfy,
                           float dfz, bool safe, bool &hit_l, bool &hit_r) {
-    const float lmax = q1.z, rmin = q1.w;
     if (safe) {
-        float t1 = XMUL(XSUB(q0.x, r.ox), dfx), t2 = XMUL(XSUB(q0.w, r.ox), dfx);
-        float t3 = XMUL(XSUB(q0.y, r.oy), dfy), t4 = XMUL(XSUB(q1.x, r.oy), dfy);
-        float t5 = XMUL(XSUB(q0.z, r.oz), dfz), t6 = XMUL(XSUB(q1.y, r.oz), dfz);
-        float mnx = SQT_FMIN(t1, t2), mxx = SQT_FMAX(t1, t2);
-        float mny = SQT_FMIN(t3, t4), mxy = SQT_FMAX(t3, t4);
-        float mnz = SQT_FMIN(t5, t6), mxz = SQT_FMAX(t5, t6);
-        float o_ax = sel3(ax, r.ox, r.oy, r.oz), df_ax = sel3(ax, dfx, dfy, dfz);
-        float tlo = sel3(ax, t1, t3, t5), thi = sel3(ax, t2, t4, t6);
-        float tlm = XMUL(XSUB(lmax, o_ax), df_ax), trm = XMUL(XSUB(rmin, o_ax), df_ax);
-        // the two axes that are not split
-        float mn_o = sel3(ax, SQT_FMAX(mny, mnz), SQT_FMAX(mnx, mnz), SQT_FMAX(mnx, mny));
-        float mx_o = sel3(ax, SQT_FMIN(mxy, mxz), SQT_FMIN(mxx, mxz), SQT_FMIN(mxx, mxy));
-        float tmin_l = SQT_FMAX(mn_o, SQT_FMIN(tlo, tlm)), tmax_l = SQT_FMIN(mx_o, SQT_FMAX(tlo, tlm));
-        float tmin_r = SQT_FMAX(mn_o, SQT_FMIN(trm, thi)), tmax_r = SQT_FMIN(mx_o, SQT_FMAX(trm, thi));
+        const float lx = XMUL(XSUB(q0.x, r.ox), dfx), ly = XMUL(XSUB(q0.y, r.oy), dfy), lz = XMUL(XSUB(q0.z, r.oz), dfz);
+        const float hx = XMUL(XSUB(q0.w, r.ox), dfx), hy = XMUL(XSUB(q1.x, r.oy), dfy), hz = XMUL(XSUB(q1.y, r.oz), dfz);
+        const float ax_ = XMUL(XSUB(q1.z, r.ox), dfx), ay = XMUL(XSUB(q1.w, r.oy), dfy), az = XMUL(XSUB(q2.x, r.oz), dfz);
+        const float bx = XMUL(XSUB(q2.y, r.ox), dfx), by = XMUL(XSUB(q2.z, r.oy), dfy), bz = XMUL(XSUB(q2.w, r.oz), dfz);
+        const float tmin_l = SQT_FMAX(SQT_FMAX(SQT_FMIN(lx, ax_), SQT_FMIN(ly, ay)), SQT_FMIN(lz, az));
+        const float tmax_l = SQT_FMIN(SQT_FMIN(SQT_FMAX(lx, ax_), SQT_FMAX(ly, ay)), SQT_FMAX(lz, az));
+        const float tmin_r = SQT_FMAX(SQT_FMAX(SQT_FMIN(bx, hx), SQT_FMIN(by, hy)), SQT_FMIN(bz, hz));
+        const float tmax_r = SQT_FMIN(SQT_FMIN(SQT_FMAX(bx, hx), SQT_FMAX(by, hy)), SQT_FMAX(bz, hz));
         hit_l = tmax_l > 0.0f && tmin_l < tmax_l;
         hit_r = tmax_r > 0.0f && tmin_r < tmax_r;
     } else {
-        float lx = q0.x, ly = q0.y, lz = q0.z, hx = q0.w, hy = q1.x, hz = q1.y;
-        hit_l = slab_exact(lx, ly, lz, ax == 0 ? lmax : hx, ax == 1 ? lmax : hy, ax == 2 ? lmax : hz, r, dfx, dfy, dfz);
-        hit_r = slab_exact(ax == 0 ? rmin : lx, ax == 1 ? rmin : ly, ax == 2 ? rmin : lz, hx, hy, hz, r, dfx, dfy, dfz);
+        hit_l = slab_exact(q0.x, q0.y, q0.z, q1.z, q1.w, q2.x, r, dfx, dfy, dfz);
+        hit_r = slab_exact(q2.y, q2.z, q2.w, q0.w, q1.x, q1.y, r, dfx, dfy, dfz);
     }
 }
 
@@ -197,12 +214,12 @@ SQT_HD bool moller_trumbore(const float4 &a0, const float4 &a1, const float4 &a2
 //
 // The machine is cut into three kinds of unit step so that a warp can run them in lock step
 // (sqt_backend.cu: all lanes do traversal steps together, then all lanes do triangle steps together):
-//   ST_DESC  enter subtree (child, meta): a Branch -> test both child boxes, pick the next subtree;
-//            a Leaf -> become ST_LEAF
+//   ST_DESC  enter subtree (child, meta), a Branch: test both child boxes, pick the next subtree
+//   ST_ENTER enter subtree (child, meta), a Leaf: fetch its record, (conservatively) cull it or become ST_LEAF
 //   ST_LEAF  test ONE triangle of the current leaf, walking from the last to the first
 //   ST_RET   a subtree returned `cur`: pop ONE stack entry and act on it
 //   ST_DONE  the ray is finished, result in `cur`
-enum : int { ST_DONE = 0, ST_DESC = 1, ST_LEAF = 2, ST_RET = 3, ST_EXIT = 4 };
+enum : int { ST_DONE = 0, ST_DESC = 1, ST_LEAF = 2, ST_RET = 3, ST_EXIT = 4, ST_ENTER = 5 };
 
 struct TravLane {
     Ray r;
@@ -212,6 +229,8 @@ struct TravLane {
     Hit cur;                    // result of the subtree that just returned / running best of the current leaf
     int sp;
     int state;
+    uint32_t sgn;               // bit k set iff dir[k] > 0 (leftToRight on axis k, BIH.hs:127)
+    float dfac;                 // |d|_1 * (1 + |d|_1), factor of the leaf-culling error bound
     bool safe;
     uint32_t *stack;            // kStackWords words of lane-private (local) memory, owned by the caller
 };
@@ -233,37 +252,79 @@ SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
              finite_f(L.r.dz) && finite_f(L.r.ox) && finite_f(L.r.oy) && finite_f(L.r.oz);
     if (!slab_exact(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], L.r, L.dfx,
                     L.dfy, L.dfz)) { L.state = ST_DONE; return; }          // BIH.hs:112 at the root
+    L.sgn = (L.r.dx > 0.0f ? 1u : 0u) | (L.r.dy > 0.0f ? 2u : 0u) | (L.r.dz > 0.0f ? 4u : 0u);
+    { const float d1 = fabsf(L.r.dx) + fabsf(L.r.dy) + fabsf(L.r.dz); L.dfac = d1 * (1.0f + d1); }
     L.child = 0u; L.meta = 0u; L.state = ST_DESC;
 }
 
+// Entering Leaf `L.child` (index into the leaf array) with `count` triangles (BIH.hs:105-109).
+//
+// Conservative leaf culling (not in the reference; exact by a forward error bound).  A triangle test can
+// only return Just if |a| >= 1e-4 and the computed u, v, u+v pass their guards and t > 1e-4
+// (Geometry.hs:117-142).  With binary32 unit roundoff eps = 2^-24 and the triangle spanned by (v0, e1, e2),
+// the computed u, v, t differ from their exact values by at most c*eps*|d|*E*(|s|+E)/|a| (E = longest edge,
+// s = origin - v0, c < 8: every numerator is a 3-term dot of a 2-term cross).  Hence an accepted hit lies,
+// in exact arithmetic, within  2*c*eps/1e-4 * |d|*(1+|d|)*E^2*(|s|+E) < 0.01*|d|(1+|d|)E^2(|s|+E)  of the
+// triangle, with the ray origin at most that far behind it.  The leaf is skipped only if the ray misses the
+// leaf's tight box enlarged by THREE times that bound (K = 0.03, norms over-estimated by 1-norms) plus
+// 1e-4 + 2^-20*max|coordinate|: no skipped triangle could have been accepted, so the traversal result is
+// bit-identical (tests: culling on/off agree on every ray; both agree with the oracle).
+// Rays with a zero/denormal/non-finite direction component (`safe` false) are never culled.
 template <bool COUNT>
-SQT_HD void enter_leaf(TravLane &L, Counters *cn) {
+SQT_HD void enter_step(const SceneView &sc, TravLane &L, Counters *cn) {
     const uint32_t count = L.meta & kCountMask;
-    if (COUNT) cn->tri_tests += count;
     L.cur.tri = -1;
+    if (count == 0u) { L.state = ST_RET; return; }                        // empty leaf -> Nothing (BIH.hs:107)
+    const float4 *lp = sc.leaves + 2 * (size_t)L.child;
+    const float4 b0 = SQT_LDG4(lp), b1 = SQT_LDG4(lp + 1);
+    if (sc.leaf_cull && L.safe) {
+        const float E = b1.z;
+        const float s1 = fabsf(L.r.ox - 0.5f * (b0.x + b0.w)) + fabsf(L.r.oy - 0.5f * (b0.y + b1.x)) +
+                         fabsf(L.r.oz - 0.5f * (b0.z + b1.y)) + ((b0.w - b0.x) + (b1.x - b0.y) + (b1.y - b0.z));
+        const float cmax = fmaxf(fmaxf(fmaxf(fabsf(b0.x), fabsf(b0.w)), fmaxf(fabsf(b0.y), fabsf(b1.x))), fmaxf(fabsf(b0.z), fabsf(b1.y)));
+        const float m = 0.03f * (s1 + E) * L.dfac * (E * E) + (1.0e-4f + 9.5367431640625e-7f * (cmax + s1));
+        const float lx = (b0.x - m - L.r.ox) * L.dfx, hx = (b0.w + m - L.r.ox) * L.dfx;
+        const float ly = (b0.y - m - L.r.oy) * L.dfy, hy = (b1.x + m - L.r.oy) * L.dfy;
+        const float lz = (b0.z - m - L.r.oz) * L.dfz, hz = (b1.y + m - L.r.oz) * L.dfz;
+        const float tmin = SQT_FMAX(SQT_FMAX(SQT_FMIN(lx, hx), SQT_FMIN(ly, hy)), SQT_FMIN(lz, hz));
+        const float tmax = SQT_FMIN(SQT_FMIN(SQT_FMAX(lx, hx), SQT_FMAX(ly, hy)), SQT_FMAX(lz, hz));
+        // keep the leaf unless the ray clearly misses; a NaN (cannot happen for safe rays) keeps it too
+        if (tmax < 0.0f || tmin > tmax) {
+            if (COUNT) cn->leaves_culled += 1;
+            L.state = ST_RET;
+            return;
+        }
+    }
+    if (COUNT) cn->tri_tests += count;
+    L.child = f2u(b1.w);
     L.i = (int)count - 1;
-    L.state = count ? ST_LEAF : ST_RET;          // empty leaf -> Nothing (BIH.hs:107)
+    L.state = ST_LEAF;
 }
 
 template <bool COUNT>
 SQT_HD void desc_step(const SceneView &sc, TravLane &L, Counters *cn) {
-    if (L.meta & kLeaf) { enter_leaf<COUNT>(L, cn); return; }
-    const float4 *np = sc.nodes + 3 * (size_t)L.child;
-    const float4 q0 = SQT_LDG4(np), q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
-    const uint32_t left = f2u(q2.x), right = f2u(q2.y), lmeta = f2u(q2.z), rmeta = f2u(q2.w);
-    const int ax = (int)((lmeta >> kAxisShift) & 3u);
+    const float4 *np = sc.nodes + kNodeQuads * (size_t)L.child;
+    const float4 q0 = SQT_LDG4(np), q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2), q3 = SQT_LDG4(np + 3);
+    const uint32_t left = f2u(q3.x), right = f2u(q3.y), lmeta = f2u(q3.z), rmeta = f2u(q3.w);
+    const uint32_t ax = (lmeta >> kAxisShift) & 3u;
     bool hit_l, hit_r;
-    slab_children(q0, q1, ax, L.r, L.dfx, L.dfy, L.dfz, L.safe, hit_l, hit_r);
+    slab_children(q0, q1, q2, L.r, L.dfx, L.dfy, L.dfz, L.safe, hit_l, hit_r);
     if (COUNT) { cn->branch_visits += 1; cn->child_box_tests += 2; }
-    const bool ltr = sel3(ax, L.r.dx, L.r.dy, L.r.dz) > 0.0f;              // BIH.hs:127
-    const uint32_t lm = lmeta & ~(3u << kAxisShift);
-    if (hit_l && hit_r) {
-        L.stack[L.sp++] = L.child;                                          // phase A frame
-        if (ltr) { L.child = left; L.meta = lm; } else { L.child = right; L.meta = rmeta; }
-    } else if (hit_l) { L.child = left; L.meta = lm; }
-    else if (hit_r) { L.child = right; L.meta = rmeta; }
-    else { L.cur.tri = -1; L.state = ST_RET; return; }
-    if (L.meta & kLeaf) enter_leaf<COUNT>(L, cn);
+    if (!(hit_l || hit_r)) { L.cur.tri = -1; L.state = ST_RET; return; }
+    const bool ltr = ((L.sgn >> ax) & 1u) != 0u;                            // BIH.hs:127
+    const bool both = hit_l && hit_r;
+    const bool go_left = both ? ltr : hit_l;                                // near child first (BIH.hs:124-126)
+    const uint32_t lm = lmeta & (kLeaf | kCountMask);
+    if (both) {                                                             // phase A frame: what ret_step needs later
+        const float lmax = sel3((int)ax, q1.z, q1.w, q2.x), rmin = sel3((int)ax, q2.y, q2.z, q2.w);
+        L.stack[L.sp] = f2u(ltr ? rmin : lmax);
+        L.stack[L.sp + 1] = ltr ? right : left;
+        L.stack[L.sp + 2] = (ltr ? rmeta : lm) | (ax << kAxisShift) | (ltr ? kLtr : 0u);
+        L.sp += 3;
+    }
+    L.child = go_left ? left : right;
+    L.meta = go_left ? lm : rmeta;
+    if (L.meta & kLeaf) L.state = ST_ENTER;
 }
 
 // One triangle of the leaf (BIH.hs:105-109): V.mapMaybe over the leaf's triangles, minimumBy (comparing dist).
@@ -280,32 +341,30 @@ SQT_HD void tri_step(const SceneView &sc, TravLane &L) {
     if (--L.i < 0) L.state = ST_RET;
 }
 
+// A subtree returned `cur`: pop entries until one of them sends the lane into a far subtree (-> ST_DESC) or
+// the stack is empty (-> ST_DONE).  Pops that only merge or propagate are a handful of instructions each.
 SQT_HD void ret_step(const SceneView &sc, TravLane &L) {
-    if (L.sp == 0) { L.state = ST_DONE; return; }
-    const uint32_t top = L.stack[L.sp - 1];
-    if (top & kPhaseB) {                                                    // far subtree returned: min' near far
-        Hit rn; rn.tri = (int)(top & ~kPhaseB); rn.dist = u2f(L.stack[L.sp - 2]); rn.t = u2f(L.stack[L.sp - 3]);
+    for (;;) {
+        if (L.sp == 0) { L.state = ST_DONE; return; }
+        const uint32_t w0 = L.stack[L.sp - 3], w1 = L.stack[L.sp - 2], w2 = L.stack[L.sp - 1];
         L.sp -= 3;
-        if (L.cur.tri < 0 || !cmp_gt(rn.dist, L.cur.dist)) L.cur = rn;
+        if (w2 & kPhaseB) {                                                 // far subtree returned: min' near far
+            if (L.cur.tri < 0 || !cmp_gt(u2f(w1), L.cur.dist)) { L.cur.tri = (int)(w2 & ~kPhaseB); L.cur.dist = u2f(w1); L.cur.t = u2f(w0); }
+            continue;
+        }
+        // near subtree returned
+        if (L.cur.tri >= 0) {
+            const int ax = (int)((w2 >> kAxisShift) & 3u);
+            const float p = XADD(sel3(ax, L.r.ox, L.r.oy, L.r.oz), XMUL(L.cur.t, sel3(ax, L.r.dx, L.r.dy, L.r.dz)));   // intersectPoint on ax
+            const bool close = (w2 & kLtr) ? (p < u2f(w0)) : (p > u2f(w0));  // BIH.hs:121-123
+            if (close) continue;
+            L.stack[L.sp] = f2u(L.cur.t); L.stack[L.sp + 1] = f2u(L.cur.dist); L.stack[L.sp + 2] = (uint32_t)L.cur.tri | kPhaseB;
+            L.sp += 3;
+        }
+        L.child = w1; L.meta = w2 & (kLeaf | kCountMask);
+        L.state = (w2 & kLeaf) ? ST_ENTER : ST_DESC;
         return;
     }
-    L.sp -= 1;                                                              // near subtree of branch `top` returned
-    const float4 *np = sc.nodes + 3 * (size_t)top;
-    const float4 q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
-    const uint32_t lmeta = f2u(q2.z);
-    const int ax = (int)((lmeta >> kAxisShift) & 3u);
-    const float d_ax = sel3(ax, L.r.dx, L.r.dy, L.r.dz);
-    const bool ltr = d_ax > 0.0f;
-    if (L.cur.tri >= 0) {
-        const float p = XADD(sel3(ax, L.r.ox, L.r.oy, L.r.oz), XMUL(L.cur.t, d_ax));   // intersectPoint on ax
-        const bool close = ltr ? (p < q1.w) : (p > q1.z);                   // BIH.hs:121-123
-        if (close) return;
-        L.stack[L.sp] = f2u(L.cur.t); L.stack[L.sp + 1] = f2u(L.cur.dist); L.stack[L.sp + 2] = (uint32_t)L.cur.tri | kPhaseB;
-        L.sp += 3;
-    }
-    if (ltr) { L.child = f2u(q2.y); L.meta = f2u(q2.w); }
-    else { L.child = f2u(q2.x); L.meta = lmeta & ~(3u << kAxisShift); }
-    L.state = ST_DESC;
 }
 
 // one lane alone, to completion (host emulation and the odd single ray)
@@ -319,6 +378,7 @@ SQT_HD Hit traverse(const SceneView &sc, const Ray &r, Counters *cn) {
     while (L.state != ST_DONE) {
         if (L.state == ST_RET) ret_step(sc, L);
         if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
+        if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, cn);
         if (L.state == ST_LEAF) tri_step(sc, L);
     }
     return L.cur;

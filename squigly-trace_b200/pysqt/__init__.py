@@ -27,7 +27,7 @@ SQT_COMM_ID_BYTES = 128
 ABI_SYMBOLS = [
     "sqt_abi_version", "sqt_create", "sqt_destroy", "sqt_last_error", "sqt_upload_scene", "sqt_intersect_batch",
     "sqt_render", "sqt_render_resident", "sqt_download_image", "sqt_tone_map", "sqt_comm_unique_id", "sqt_comm_init",
-    "sqt_comm_init_all", "sqt_render_group", "sqt_measure_fp32_peak", "sqt_measure_l2_bandwidth", "sqt_device_info",
+    "sqt_comm_init_all", "sqt_render_group", "sqt_measure_fp32_peak", "sqt_measure_l2_bandwidth", "sqt_device_info", "sqt_set_option",
 ]
 
 
@@ -67,7 +67,7 @@ class Stats(C.Structure):
     _fields_ = [("device_ms", C.c_double), ("primary_ms", C.c_double), ("paths_ms", C.c_double), ("tonemap_ms", C.c_double),
                 ("reduce_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("rays_traced", C.c_uint64),
                 ("rays_reference", C.c_uint64), ("samples", C.c_uint64), ("branch_visits", C.c_uint64),
-                ("child_box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("child_box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("leaves_culled", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
@@ -112,6 +112,7 @@ def b200():
         L.sqt_render_group.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sqt_measure_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.sqt_measure_l2_bandwidth.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.sqt_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.sqt_device_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p]
         for name in ABI_SYMBOLS:
             if name not in ("sqt_last_error",):
@@ -309,6 +310,9 @@ class Context:
         out = np.zeros(mean_rgb.shape, np.uint8)
         self._ck(self.L.sqt_tone_map(self.h, _p(mean_rgb), mean_rgb.size // 3, _p(out)), "sqt_tone_map")
         return out
+
+    def set_leaf_cull(self, on):
+        self._ck(self.L.sqt_set_option(self.h, 1, 1 if on else 0), "sqt_set_option")
 
     def comm_init(self, rank, world, uid):
         buf = (C.c_uint8 * SQT_COMM_ID_BYTES).from_buffer_copy(bytes(uid))

@@ -26,6 +26,7 @@ def emu_lib():
         E.emu_free.argtypes = [C.c_void_p]
         E.emu_height.restype = C.c_int
         E.emu_height.argtypes = [C.c_void_p]
+        E.emu_set_leaf_cull.argtypes = [C.c_void_p, C.c_int]
         E.emu_intersect_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         E.emu_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _EMU = E
@@ -54,9 +55,13 @@ class Emu:
         dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
         n = len(org)
         tri = np.zeros(n, np.int32); dist = np.zeros(n, np.float32); pt = np.zeros((n, 3), np.float32)
-        cn = np.zeros(4, np.uint64)
+        cn = np.zeros(5, np.uint64)
         emu_lib().emu_intersect_batch(self.h, _p(org), _p(dirs), n, _p(tri), _p(dist), _p(pt), _p(cn))
-        return tri, dist, pt, dict(branch_visits=int(cn[0]), child_box_tests=int(cn[1]), tri_tests=int(cn[2]), rays=int(cn[3]))
+        return tri, dist, pt, dict(branch_visits=int(cn[0]), child_box_tests=int(cn[1]), tri_tests=int(cn[2]), rays=int(cn[3]),
+                                   leaves_culled=int(cn[4]))
+
+    def set_leaf_cull(self, on):
+        emu_lib().emu_set_leaf_cull(self.h, 1 if on else 0)
 
     def render(self, cam12, params, rank=0, world=1):
         acc = np.zeros((params.rows, params.cols, 3), np.float32)

@@ -33,7 +33,8 @@ emu_scene *emu_upload(const sqt_scene_desc *d) {
     s->tris.resize((size_t)3 * (d->n_tris ? d->n_tris : 1));
     if (d->n_tris) std::memcpy(s->tris.data(), d->tris, (size_t)d->n_tris * 48);
     SceneView v = {};
-    v.nodes = s->lay.nodes.data(); v.tris = s->tris.data(); v.mats = s->lay.mats.data();
+    v.nodes = s->lay.nodes.data(); v.tris = s->tris.data(); v.mats = s->lay.mats.data(); v.leaves = s->lay.leaves.data();
+    v.leaf_cull = 1;
     for (int k = 0; k < 3; ++k) { v.root_lo[k] = d->root_bounds[k]; v.root_hi[k] = d->root_bounds[3 + k]; }
     v.n_branches = s->lay.n_branches; v.n_tris = d->n_tris; v.n_mats = d->n_mats;
     v.root_is_leaf = (d->nodes[0].b & SQT_NODE_LEAF) ? 1u : 0u;
@@ -43,14 +44,15 @@ emu_scene *emu_upload(const sqt_scene_desc *d) {
 const char *emu_error(emu_scene *s) { return s->err.c_str(); }
 void emu_free(emu_scene *s) { delete s; }
 int emu_height(emu_scene *s) { return (int)s->lay.height; }
+void emu_set_leaf_cull(emu_scene *s, int on) { s->view.leaf_cull = on ? 1u : 0u; }
 
 void emu_intersect_batch(emu_scene *s, const float *org, const float *dir, long long n, int *tri_out, float *dist_out,
-                         float *point_out, unsigned long long *counters4) {
-    Counters cn = {0, 0, 0, 0};
+                         float *point_out, unsigned long long *counters4 /* 5 values */) {
+    Counters cn = {0, 0, 0, 0, 0};
     PathStats st = {0, 0, 0};
     const long long n_lanes = 5;
     for (long long l = 0; l < n_lanes; ++l) { BatchPolicy pol(org, dir, n, l, n_lanes, tri_out, dist_out, point_out, st); run_lane<true>(s->view, pol, &cn); }
-    if (counters4) { counters4[0] = cn.branch_visits; counters4[1] = cn.child_box_tests; counters4[2] = cn.tri_tests; counters4[3] = cn.rays; }
+    if (counters4) { counters4[0] = cn.branch_visits; counters4[1] = cn.child_box_tests; counters4[2] = cn.tri_tests; counters4[3] = cn.rays; counters4[4] = cn.leaves_culled; }
 }
 
 // One render.  The device runs 32 lanes per warp in lock step; lanes are independent, so here `n_lanes` software
@@ -68,7 +70,7 @@ void emu_render(emu_scene *s, const sqt_camera *cam, const sqt_render_params *p,
     d.terminate_on_black = (s->lay.terminate_on_black_ok && !(p->flags & SQT_F_NO_EARLY_TERMINATION)) ? 1 : 0;
     const long long npix = (long long)d.rows * d.cols, nwork = work_items(d);
     std::memset(accum, 0, (size_t)npix * 12);
-    Counters cn = {0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0};
     PathStats st = {0, 0, 0};
     const long long n_lanes = 7;
     if (d.mode == 1) {
@@ -95,6 +97,96 @@ void emu_render(emu_scene *s, const sqt_camera *cam, const sqt_render_params *p,
             tone_map(XMUL(inv, accum[3 * i]), XMUL(inv, accum[3 * i + 1]), XMUL(inv, accum[3 * i + 2]), rgb8 + 3 * i);
     }
     if (stats5) { stats5[0] = st.rays; stats5[1] = st.samples; stats5[2] = st.primary_reused; stats5[3] = cn.branch_visits; stats5[4] = cn.tri_tests; }
+}
+
+// Step trace of one path lane that renders the pixels [w0, w1) in order: one byte per unit step
+// ('R' regeneration, 'T' traversal step, 'L' triangle step).  Used by tools/sched_sim.py to study warp
+// schedulers offline.  Returns the number of bytes written (truncated at cap).
+long long emu_trace_lane(emu_scene *s, const sqt_camera *cam, const sqt_render_params *p, long long w0, long long w1,
+                         unsigned char *out, long long cap) {
+    RenderParams d = {};
+    d.rows = p->rows; d.cols = p->cols; d.xdiv = p->xdiv; d.ydiv = p->ydiv; d.seed_stride = p->seed_stride;
+    d.spp = p->spp; d.max_depth = p->max_depth; d.mode = 0; d.seed = p->seed; d.rank = 0; d.world = 1;
+    d.primary_reuse = 1;
+    for (int k = 0; k < 3; ++k) d.cam_pos[k] = cam->position[k];
+    for (int k = 0; k < 9; ++k) d.cam_rot[k] = cam->rotation[k];
+    d.terminate_on_black = s->lay.terminate_on_black_ok;
+    const long long npix = (long long)d.rows * d.cols;
+    std::vector<int2> prim((size_t)npix);
+    Counters cn = {0, 0, 0, 0, 0};
+    PathStats st = {0, 0, 0};
+    for (long long w = w0; w < w1; ++w) {
+        const Ray r = make_ray(d, (int)(w / d.cols), (int)(w % d.cols));
+        const Hit h = traverse<false>(s->view, r, &cn);
+        prim[(size_t)w].x = h.tri; prim[(size_t)w].y = (int)f2u(h.t);
+    }
+    std::vector<float> accum((size_t)npix * 3);
+    SeqFetch fetch{w0, w1};
+    uint16_t pm[SQT_MAX_DEPTH];
+    PathPolicy<SeqFetch> pol(d, prim.data(), accum.data(), fetch, st, pm);
+    uint32_t stack[kStackWords];
+    TravLane L;
+    L.stack = stack; L.state = ST_DONE; L.sp = 0; L.cur.tri = -1;
+    long long n = 0;
+    for (;;) {
+        if (L.state == ST_DONE) { pol.regen<false>(s->view, L, &cn); if (n < cap) out[n] = 'R'; n++; }
+        if (L.state == ST_EXIT) break;
+        if (L.state == ST_RET || L.state == ST_DESC) {
+            if (L.state == ST_RET) ret_step(s->view, L);
+            if (L.state == ST_DESC) desc_step<false>(s->view, L, &cn);
+            if (n < cap) out[n] = 'T'; n++;
+        } else if (L.state == ST_ENTER) { enter_step<false>(s->view, L, &cn); if (n < cap) out[n] = 'E'; n++; }
+        else if (L.state == ST_LEAF) { tri_step(s->view, L); if (n < cap) out[n] = 'L'; n++; }
+    }
+    return n < cap ? n : cap;
+}
+
+// Diagnostic for DESIGN.md: how many leaf visits would a (conservatively enlarged) tight leaf bounding box reject?
+// out = { leaf visits, triangle tests, visits whose ray misses the enlarged tight box, triangle tests in those,
+//         visits with at least one accepted triangle, of those rejected by the box (must be 0) }
+void emu_leaf_cull_stats(emu_scene *s, const float *org, const float *dir, long long n, float margin, unsigned long long *out) {
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    const uint32_t saved_cull = s->view.leaf_cull;
+    s->view.leaf_cull = 0;
+    Counters cn = {0, 0, 0, 0, 0};
+    uint32_t stack[kStackWords];
+    for (long long i = 0; i < n; ++i) {
+        TravLane L; L.stack = stack;
+        L.r = Ray{org[3 * i], org[3 * i + 1], org[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+        start_ray<false>(s->view, L, &cn);
+        while (L.state != ST_DONE) {
+            if (L.state == ST_RET) ret_step(s->view, L);
+            if (L.state == ST_DESC) desc_step<false>(s->view, L, &cn);
+            if (L.state == ST_ENTER) enter_step<false>(s->view, L, &cn);
+            if (L.state == ST_LEAF) {
+                const uint32_t first = L.child, count = (uint32_t)L.i + 1;
+                float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+                for (uint32_t t = 0; t < count; ++t) {
+                    const float4 a0 = s->tris[3 * (size_t)(first + t)], a1 = s->tris[3 * (size_t)(first + t) + 1], a2 = s->tris[3 * (size_t)(first + t) + 2];
+                    const float v[3][3] = {{a0.x, a0.y, a0.z}, {a0.x + a0.w, a0.y + a1.x, a0.z + a1.y}, {a0.x + a1.z, a0.y + a1.w, a0.z + a2.x}};
+                    for (int q = 0; q < 3; ++q) for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], v[q][c]); hi[c] = std::max(hi[c], v[q][c]); }
+                }
+                float E2 = 0;
+                for (uint32_t t = 0; t < count; ++t) {
+                    const float4 a0 = s->tris[3 * (size_t)(first + t)], a1 = s->tris[3 * (size_t)(first + t) + 1], a2 = s->tris[3 * (size_t)(first + t) + 2];
+                    const float e1[3] = {a0.w, a1.x, a1.y}, e2[3] = {a1.z, a1.w, a2.x};
+                    float l1 = 0, l2 = 0, l3 = 0;
+                    for (int c = 0; c < 3; ++c) { l1 += e1[c] * e1[c]; l2 += e2[c] * e2[c]; l3 += (e2[c] - e1[c]) * (e2[c] - e1[c]); }
+                    E2 = std::max(E2, std::max(l1, std::max(l2, l3)));
+                }
+                const float E = std::sqrt(E2);
+                const float s1 = std::fabs(L.r.ox - 0.5f * (lo[0] + hi[0])) + std::fabs(L.r.oy - 0.5f * (lo[1] + hi[1])) + std::fabs(L.r.oz - 0.5f * (lo[2] + hi[2])) + (hi[0] - lo[0]) + (hi[1] - lo[1]) + (hi[2] - lo[2]);
+                const float d1 = std::fabs(L.r.dx) + std::fabs(L.r.dy) + std::fabs(L.r.dz);
+                const float m = margin * (s1 + E) * d1 * (1.0f + d1) * E2 + 1e-4f;
+                const bool box_hit = slab_exact(lo[0] - m, lo[1] - m, lo[2] - m, hi[0] + m, hi[1] + m, hi[2] + m, L.r, L.dfx, L.dfy, L.dfz);
+                while (L.state == ST_LEAF) tri_step(s->view, L);
+                out[0] += 1; out[1] += count;
+                if (!box_hit) { out[2] += 1; out[3] += count; }
+                if (L.cur.tri >= 0) { out[4] += 1; if (!box_hit) out[5] += 1; }
+            }
+        }
+    }
+    s->view.leaf_cull = saved_cull;
 }
 
 }  // extern "C"

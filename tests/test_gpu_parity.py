@@ -4,6 +4,8 @@ Bar: bit-exact for hit index, dist, hit point, the float accumulation buffer and
 index work and -- because the oracle restates the device's "sqt trig" polynomials and shares the counter-based
 RNG -- the floating-point image too).  Against the reference-faithful libm oracle the bar is a stated RMSE.
 """
+import contextlib
+
 import numpy as np
 import pytest
 
@@ -16,6 +18,17 @@ from common import adversarial_rays, assert_same_hits, bits, build_pair, random_
 pytestmark = pytest.mark.gpu
 
 
+@contextlib.contextmanager
+def no_leaf_cull(ctx):
+    """The conservative leaf culling skips triangle tests the reference performs; switch it off where the test
+    compares work counters with the oracle's."""
+    ctx.set_leaf_cull(False)
+    try:
+        yield
+    finally:
+        ctx.set_leaf_cull(True)
+
+
 def test_device_is_b200(gpu_ctx):
     info = gpu_ctx.info()
     assert info["cc"][0] == 10, info
@@ -26,8 +39,10 @@ def test_device_is_b200(gpu_ctx):
 def test_primary_rays_bit_exact(gpu_ctx, host_scene, oracle_scene, camera):
     gpu_ctx.upload(host_scene)
     org, dirs = O.make_rays(O.make_params(540, 540, 1), camera)
-    got = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
     want = oracle_scene.intersect_batch(org, dirs, counters=True)
+    assert_same_hits(gpu_ctx.intersect_batch(org, dirs), want, "primary 540x540 (leaf culling on)")
+    with no_leaf_cull(gpu_ctx):
+        got = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
     assert_same_hits(got, want, "primary 540x540")
     st, cn = got[3], want[3]
     # the traversal visits exactly the reference's subtrees: same branch visits and triangle tests
@@ -76,6 +91,21 @@ def test_recorded_bounce_rays(gpu_ctx, host_scene, oracle_scene, camera):
     d2 = rng.normal(size=(hit.sum(), 3)).astype(np.float32)
     d2 /= np.linalg.norm(d2, axis=1, keepdims=True).astype(np.float32)
     assert_same_hits(gpu_ctx.intersect_batch(point[hit], d2), oracle_scene.intersect_batch(point[hit], d2), "bounce")
+
+
+def test_leaf_culling_changes_no_result(gpu_ctx, host_scene, camera):
+    """2M incoherent + 1M camera rays: identical index, dist and point bits with the culling on and off, and the
+    culling really skips work."""
+    gpu_ctx.upload(host_scene)
+    org, dirs = random_rays(2_000_000, seed=99)
+    o2, d2 = O.make_rays(O.make_params(1000, 1000, 1), camera)
+    org = np.concatenate([org, o2]); dirs = np.concatenate([dirs, d2])
+    on = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
+    with no_leaf_cull(gpu_ctx):
+        off = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
+    assert_same_hits(on, off, "cull on vs off")
+    assert on[3]["leaves_culled"] > 0 and off[3]["leaves_culled"] == 0
+    assert on[3]["tri_tests"] < 0.8 * off[3]["tri_tests"]
 
 
 def test_empty_batch_and_errors(gpu_ctx, host_scene):
@@ -128,10 +158,14 @@ def test_synthetic_scenes_bit_exact(gpu_ctx, gen, n):
     osc, hs = build_pair(v9, mi, mats)
     gpu_ctx.upload(hs)
     org, dirs = random_rays(100_000, seed=21, lo=-1.5, hi=1.5)
-    got = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
     want = osc.intersect_batch(org, dirs, counters=True)
+    culled = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
+    assert_same_hits(culled, want, gen + " (leaf culling on)")
+    with no_leaf_cull(gpu_ctx):
+        got = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
     assert_same_hits(got, want, gen)
     assert got[3]["tri_tests"] == int(want[3][3]) and got[3]["branch_visits"] == int(want[3][0])
+    assert culled[3]["branch_visits"] == got[3]["branch_visits"] and culled[3]["tri_tests"] <= got[3]["tri_tests"]
 
 
 # ------------------------------------------------------------------ rendered image
@@ -152,7 +186,8 @@ def test_render_reference_work_flags_match_oracle_counts(gpu_ctx, host_scene, or
     branch visits and triangle tests equal the oracle's counters."""
     gpu_ctx.upload(host_scene)
     f = pysqt.SQT_F_NO_PRIMARY_REUSE | pysqt.SQT_F_NO_EARLY_TERMINATION | pysqt.SQT_F_COUNT_WORK
-    out = gpu_ctx.render(camera, pysqt.make_params(72, 56, 6, max_depth=4, seed=9, flags=f))
+    with no_leaf_cull(gpu_ctx):
+        out = gpu_ctx.render(camera, pysqt.make_params(72, 56, 6, max_depth=4, seed=9, flags=f))
     ref = oracle_scene.render(camera, O.make_params(72, 56, 6, max_depth=4, seed=9, trig=1))
     assert np.array_equal(bits(out["accum"]), bits(ref["accum"]))
     st, cn = out["stats"], ref["counters"]

@@ -1,0 +1,191 @@
+"""Offline study of warp schedulers for the persistent traversal loop.
+
+Records, with the host build of the kernel logic (tests/emu), the exact sequence of unit steps every lane of a
+warp would execute for data/scene.obj (R = regeneration, T = traversal step, L = triangle test), then replays 32
+such lanes under different scheduling policies and reports issue slots per ray.  A policy only changes the ORDER
+in which lanes are served, so any policy is valid; the cost model charges each executed phase iteration its
+instruction count regardless of how many lanes are active (that is what SIMT does).
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "squigly-trace_b200"), os.path.join(ROOT, "tests")]
+import pysqt
+from common import emu_lib, Emu
+
+COST = {"T": 85, "E": 50, "L": 62, "R": 650}     # instructions per step body (from SASS / ncu)
+VOTE = 6                                   # ballot + popc + compare + branch per inner iteration
+OUTER = 30                                 # one trip around the outer loop
+
+
+def traces(n_lanes=32, pixels_per_lane=6, spp=8, depth=8, W=480, H=270):
+    data = os.path.join(ROOT, "data")
+    hs = pysqt.HostScene.load(os.path.join(data, "scene.obj"), data)
+    cam = pysqt.camera_struct(pysqt.load_camera(os.path.join(data, "camera")))
+    e = Emu(hs)
+    E = emu_lib()
+    E.emu_trace_lane.restype = C.c_longlong
+    E.emu_trace_lane.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong]
+    p = pysqt.make_params(W, H, spp, max_depth=depth, seed=0)
+    out = []
+    base = (H // 2) * W + W // 3
+    cap = 1 << 22
+    buf = np.zeros(cap, np.uint8)
+    for l in range(n_lanes):
+        w0 = base + l * pixels_per_lane
+        n = E.emu_trace_lane(e.h, C.byref(cam), C.byref(p), w0, w0 + pixels_per_lane, buf.ctypes.data_as(C.c_void_p), cap)
+        out.append(bytes(buf[:n]).decode())
+    return out
+
+
+def simulate(tr, policy, **kw):
+    """returns (cost, rays)"""
+    pos = [0] * len(tr)
+    n = len(tr)
+    cost = 0
+    rays = sum(t.count("R") for t in tr)
+
+    def state(i):
+        return tr[i][pos[i]] if pos[i] < len(tr[i]) else "X"
+
+    def run(kind):
+        nonlocal cost
+        k = 0
+        for i in range(n):
+            if state(i) == kind:
+                pos[i] += 1; k += 1
+        cost += COST[kind] + VOTE
+        return k
+
+    def count(kind):
+        return sum(1 for i in range(n) if state(i) == kind)
+
+    if policy == "phased":
+        a_leave, b_leave, c_min = kw["a_leave"], kw["b_leave"], kw["c_min"]
+        while True:
+            nd, nt, nl = count("R"), count("T"), count("L")
+            if nd + nt + nl == 0: break
+            cost += OUTER
+            if nd and (nd >= c_min or nt + nl == 0): run("R")
+            while count("T"):
+                run("T")
+                if count("T") <= a_leave: break
+            while count("L"):
+                run("L")
+                if count("L") < b_leave: break
+    elif policy == "majority":
+        wt, wl, wd, c_min = kw["wt"], kw["wl"], kw["wd"], kw["c_min"]
+        while True:
+            nd, nt, nl = count("R"), count("T"), count("L")
+            if nd + nt + nl == 0: break
+            cost += 14
+            sd = nd * wd if (nd >= c_min or nt + nl == 0) else 0
+            st, sl = nt * wt, nl * wl
+            if sl >= st and sl >= sd and nl: run("L")
+            elif st >= sd and nt: run("T")
+            else: run("R")
+    elif policy == "thresh":
+        # every trip: run each kind of step once if at least `thr` lanes want it (regen: c_min); if nothing
+        # qualified, run the most wanted kind
+        thr, c_min = kw["thr"], kw["c_min"]
+        while True:
+            cnt = {k: count(k) for k in "RTEL"}
+            if sum(cnt.values()) == 0: break
+            cost += 12
+            ran = False
+            for k in "TEL":
+                if count(k) >= thr[k]: run(k); ran = True
+            if count("R") >= c_min: run("R"); ran = True
+            if not ran:
+                cnt = {k: count(k) for k in "RTEL"}
+                run(max(cnt, key=lambda k: cnt[k]))
+    elif policy == "phased4":
+        a_leave, b_leave, c_min = kw["a_leave"], kw["b_leave"], kw["c_min"]
+        while True:
+            nd, nt, ne, nl = count("R"), count("T"), count("E"), count("L")
+            if nd + nt + ne + nl == 0: break
+            cost += OUTER
+            if nd and (nd >= c_min or nt + ne + nl == 0): run("R")
+            while True:
+                while count("T"):
+                    run("T")
+                    if count("T") <= a_leave: break
+                if count("E"): run("E")
+                if count("T") <= a_leave: break
+            while count("L"):
+                run("L")
+                if count("L") < b_leave: break
+    elif policy == "hyst":
+        # stay in a phase while it has at least `stay` lanes, switch to the fullest one otherwise
+        stay, c_min = kw["stay"], kw["c_min"]
+        cur = "T"
+        while True:
+            nd, nt, nl = count("R"), count("T"), count("L")
+            if nd + nt + nl == 0: break
+            cnt = {"R": nd if (nd >= c_min or nt + nl == 0) else 0, "T": nt, "L": nl}
+            if cnt[cur] < stay:
+                cost += OUTER
+                cur = max(cnt, key=lambda k: cnt[k])
+            run(cur)
+    return cost, rays
+
+
+if __name__ == "__main__":
+    tr = traces()
+    tot = sum(len(t) for t in tr)
+    print("lanes", len(tr), "steps", tot, {k: sum(t.count(k) for t in tr) for k in "RTEL"})
+    ideal = sum(COST[c] for t in tr for c in t) / 32
+    rays = sum(t.count("R") for t in tr)
+    print("ideal (perfect packing) slots/ray %.0f" % (ideal / rays))
+    for a, b, c in [(0, 1, 4), (4, 1, 4), (8, 8, 4), (12, 12, 4), (16, 12, 4), (12, 16, 8)]:
+        cst, r = simulate(tr, "phased4", a_leave=a, b_leave=b, c_min=c)
+        print("phased4 a_leave=%2d b_leave=%2d c_min=%2d : %6.0f slots/ray  eff %.2f" % (a, b, c, cst / r, ideal / cst))
+    for t, e, l, c in [(8, 8, 8, 4), (12, 8, 12, 4), (12, 12, 12, 8), (16, 8, 16, 8), (16, 16, 16, 8), (10, 6, 10, 6), (20, 10, 20, 8), (14, 10, 14, 10)]:
+        cst, r = simulate(tr, "thresh", thr={"T": t, "E": e, "L": l}, c_min=c)
+        print("thresh T>=%2d E>=%2d L>=%2d c_min=%2d : %6.0f slots/ray  eff %.2f" % (t, e, l, c, cst / r, ideal / cst))
+
+
+def simulate_pool(tr_all, slots=64, burst_l=4, burst_t=2, overhead=86, pick="max"):
+    """Warp-private pool: `slots` rays per warp; each round the warp takes up to 32 rays that are in the most
+    populated state and runs up to burst_* steps of that kind for each before writing them back."""
+    # tr_all: list of lane traces; we use `slots` of them as the warp's pool
+    tr = tr_all[:slots]
+    pos = [0] * len(tr)
+    cost = 0
+    rays = sum(t.count("R") for t in tr)
+
+    def state(i):
+        return tr[i][pos[i]] if pos[i] < len(tr[i]) else "X"
+    util_num = util_den = 0
+    while True:
+        groups = {"R": [], "T": [], "E": [], "L": []}
+        for i in range(len(tr)):
+            s = state(i)
+            if s != "X": groups[s].append(i)
+        if not any(groups.values()): break
+        kind = max(groups, key=lambda k: len(groups[k]) * (1 if k != "R" else 1))
+        sel = groups[kind][:32]
+        burst = {"L": burst_l, "T": burst_t, "R": 1, "E": 1}[kind]
+        cost += overhead
+        for b in range(burst):
+            act = [i for i in sel if state(i) == kind]
+            if not act: break
+            for i in act: pos[i] += 1
+            cost += COST[kind] + 4
+            util_num += len(act); util_den += 32
+    return cost, rays, util_num / max(util_den, 1)
+
+
+if __name__ == "__main__":
+    tr128 = traces(n_lanes=128, pixels_per_lane=2, spp=6)
+    ideal = sum(COST[c] for t in tr128 for c in t) / 32
+    rays = sum(t.count("R") for t in tr128)
+    print("pool study: ideal %.0f slots/ray" % (ideal / rays))
+    for slots, bl, bt, ov in [(32, 1, 1, 0), (64, 4, 2, 86), (96, 4, 2, 86), (128, 4, 2, 86), (64, 2, 1, 86), (64, 8, 3, 86), (96, 8, 3, 86),
+                              (64, 4, 2, 120), (96, 6, 2, 120), (128, 14, 4, 120)]:
+        c, r, u = simulate_pool(tr128, slots, bl, bt, ov)
+        print("pool slots=%3d burst L=%d T=%d overhead=%3d : %6.0f slots/ray  lane util %.2f" % (slots, bl, bt, ov, c / r, u))
