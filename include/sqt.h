@@ -115,6 +115,8 @@ typedef struct sqt_stats {
     uint64_t samples;            /* paths (Lib.hs:84) */
     uint64_t branch_visits, child_box_tests, tri_tests;    /* only with SQT_F_COUNT_WORK */
     uint64_t leaves_culled;      /* leaf visits skipped by the conservative tight-box test (with SQT_F_COUNT_WORK) */
+    uint64_t mt_pass_a, mt_pass_u, mt_pass_v, mt_accept;   /* triangle tests that got past the a / u / v / t guards
+                                                               of Geometry.hs:118-122 (with SQT_F_COUNT_WORK) */
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t kernel_launches;
     uint32_t reserved;

@@ -32,6 +32,7 @@ using namespace sqt;
 struct DeviceStats {
     unsigned long long rays, samples, primary_reused;
     unsigned long long branch_visits, child_box_tests, tri_tests, leaves_culled;
+    unsigned long long mt_pass_a, mt_pass_u, mt_pass_v, mt_accept;
     unsigned long long work_next;       // dynamic work counter of k_paths
 };
 
@@ -43,13 +44,17 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 __device__ __forceinline__ void flush_stats(DeviceStats *ds, const PathStats &st, const Counters &cn, bool count) {
     unsigned long long r = warp_sum(st.rays), s = warp_sum(st.samples), p = warp_sum(st.primary_reused);
     unsigned long long b = 0, c = 0, t = 0;
-    unsigned long long lc = 0;
-    if (count) { b = warp_sum(cn.branch_visits); c = warp_sum(cn.child_box_tests); t = warp_sum(cn.tri_tests); lc = warp_sum(cn.leaves_culled); }
+    unsigned long long lc = 0, ga = 0, gu = 0, gv = 0, gt = 0;
+    if (count) {
+        b = warp_sum(cn.branch_visits); c = warp_sum(cn.child_box_tests); t = warp_sum(cn.tri_tests); lc = warp_sum(cn.leaves_culled);
+        ga = warp_sum(cn.mt_pass_a); gu = warp_sum(cn.mt_pass_u); gv = warp_sum(cn.mt_pass_v); gt = warp_sum(cn.mt_accept);
+    }
     if ((threadIdx.x & 31) == 0) {
         if (r) atomicAdd(&ds->rays, r);
         if (s) atomicAdd(&ds->samples, s);
         if (p) atomicAdd(&ds->primary_reused, p);
-        if (count) { atomicAdd(&ds->branch_visits, b); atomicAdd(&ds->child_box_tests, c); atomicAdd(&ds->tri_tests, t); atomicAdd(&ds->leaves_culled, lc); }
+        if (count) { atomicAdd(&ds->branch_visits, b); atomicAdd(&ds->child_box_tests, c); atomicAdd(&ds->tri_tests, t); atomicAdd(&ds->leaves_culled, lc);
+            atomicAdd(&ds->mt_pass_a, ga); atomicAdd(&ds->mt_pass_u, gu); atomicAdd(&ds->mt_pass_v, gv); atomicAdd(&ds->mt_accept, gt); }
     }
 }
 
@@ -105,7 +110,7 @@ __device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Coun
         // ---- triangle steps
         unsigned m = __ballot_sync(FULL, L.state == ST_LEAF);
         while (m != 0u) {
-            if (L.state == ST_LEAF) tri_step(sc, L);
+            if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, cn);
             m = __ballot_sync(FULL, L.state == ST_LEAF);
             if (__popc(m) < tn.b_leave) break;
         }
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(128) k_intersect_batch(SceneView sc, const flo
                                                          const float *__restrict__ dir, long long n,
                                                          int *__restrict__ tri_out, float *__restrict__ dist_out,
                                                          float *__restrict__ point_out, DeviceStats *ds, Tune tn) {
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {};
     PathStats st = {0, 0, 0};
     BatchPolicy pol(org, dir, n, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, tri_out,
                     dist_out, point_out, st);
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(128) k_intersect_batch(SceneView sc, const flo
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_primary(SceneView sc, RenderParams p, int2 *__restrict__ prim, DeviceStats *ds, Tune tn) {
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {};
     PathStats st = {0, 0, 0};
     PrimaryPolicy pol(p, prim, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, st);
     warp_loop<COUNT>(sc, pol, &cn, tn);
@@ -151,7 +156,7 @@ struct DeviceFetch {
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, const int2 *__restrict__ prim,
                                                float *__restrict__ accum, DeviceStats *ds, Tune tn) {
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {};
     PathStats st = {0, 0, 0};
     DeviceFetch fetch = {&ds->work_next, work_items(p)};
     uint16_t pm[SQT_MAX_DEPTH];
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, con
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_raycast(SceneView sc, RenderParams p, float *__restrict__ accum, DeviceStats *ds, Tune tn) {
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {};
     PathStats st = {0, 0, 0};
     CastPolicy pol(p, accum, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, st);
     warp_loop<COUNT>(sc, pol, &cn, tn);
@@ -471,6 +476,8 @@ extern "C" int sqt_intersect_batch(sqt_ctx *ctx, const float *org, const float *
         stats->rays_traced = ctx->h_stats->rays; stats->rays_reference = ctx->h_stats->rays;
         stats->branch_visits = ctx->h_stats->branch_visits; stats->child_box_tests = ctx->h_stats->child_box_tests;
         stats->tri_tests = ctx->h_stats->tri_tests; stats->leaves_culled = ctx->h_stats->leaves_culled;
+        stats->mt_pass_a = ctx->h_stats->mt_pass_a; stats->mt_pass_u = ctx->h_stats->mt_pass_u;
+        stats->mt_pass_v = ctx->h_stats->mt_pass_v; stats->mt_accept = ctx->h_stats->mt_accept;
         stats->h2d_bytes = (uint64_t)n * 24; stats->d2h_bytes = (uint64_t)n * (4 + (dist_out ? 4 : 0) + (point_out ? 12 : 0));
         stats->kernel_launches = 1;
     }
@@ -559,6 +566,8 @@ static void fill_stats(sqt_ctx *ctx, sqt_stats *s, uint32_t launches) {
     s->rays_reference = ctx->h_stats->rays + ctx->h_stats->primary_reused;
     s->branch_visits = ctx->h_stats->branch_visits; s->child_box_tests = ctx->h_stats->child_box_tests;
     s->tri_tests = ctx->h_stats->tri_tests; s->leaves_culled = ctx->h_stats->leaves_culled;
+    s->mt_pass_a = ctx->h_stats->mt_pass_a; s->mt_pass_u = ctx->h_stats->mt_pass_u;
+    s->mt_pass_v = ctx->h_stats->mt_pass_v; s->mt_accept = ctx->h_stats->mt_accept;
     s->kernel_launches = launches;
 }
 

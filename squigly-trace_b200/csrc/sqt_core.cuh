@@ -91,7 +91,10 @@ struct SceneView {
 
 struct Ray { float ox, oy, oz, dx, dy, dz; };
 struct Hit { int tri; float t; float dist; };      // tri = index in leaf order, -1 = Nothing
-struct Counters { unsigned long long branch_visits, child_box_tests, tri_tests, rays, leaves_culled; };
+struct Counters {
+    unsigned long long branch_visits, child_box_tests, tri_tests, rays, leaves_culled;
+    unsigned long long mt_pass_a, mt_pass_u, mt_pass_v, mt_accept;      // triangle tests that got past each guard
+};
 
 SQT_HD uint32_t f2u(float f) {
 #if defined(__CUDA_ARCH__)
@@ -171,7 +174,7 @@ SQT_HD void slab_children(const float4 &q0, const float4 &q1, const float4 &q2, 
 // ------------------------------------------------------------------------- Moller-Trumbore
 // Geometry.hs:117-142 with edge1/edge2 precomputed.  Guard order a -> u -> v -> t.
 SQT_HD bool moller_trumbore(const float4 &a0, const float4 &a1, const float4 &a2, const Ray &r, float &t_out,
-                            float &dist_out) {
+                            float &dist_out, int &stage) {
     const float eps = 0.0001f;
     const float v0x = a0.x, v0y = a0.y, v0z = a0.z;
     const float e1x = a0.w, e1y = a1.x, e1z = a1.y;
@@ -181,19 +184,24 @@ SQT_HD bool moller_trumbore(const float4 &a0, const float4 &a1, const float4 &a2
     float hy = XSUB(XMUL(r.dz, e2x), XMUL(r.dx, e2z));
     float hz = XSUB(XMUL(r.dx, e2y), XMUL(r.dy, e2x));
     float a = dot3(e1x, e1y, e1z, hx, hy, hz);
+    stage = 0;
     if (a > -eps && a < eps) return false;
+    stage = 1;
     float f = XRCP(a);
     float sx = XSUB(r.ox, v0x), sy = XSUB(r.oy, v0y), sz = XSUB(r.oz, v0z);
     float u = XMUL(f, dot3(sx, sy, sz, hx, hy, hz));
     if (u < 0.0f || u > 1.0f) return false;
+    stage = 2;
     // q = s `cross` edge1
     float qx = XSUB(XMUL(sy, e1z), XMUL(sz, e1y));
     float qy = XSUB(XMUL(sz, e1x), XMUL(sx, e1z));
     float qz = XSUB(XMUL(sx, e1y), XMUL(sy, e1x));
     float v = XMUL(f, dot3(r.dx, r.dy, r.dz, qx, qy, qz));
     if (v < 0.0f || XADD(u, v) > 1.0f) return false;
+    stage = 3;
     float t = XMUL(f, dot3(e2x, e2y, e2z, qx, qy, qz));
     if (!(t > eps)) return false;
+    stage = 4;
     // outInter = rayVert + t *^ rayDir ; rayDist = norm (outInter - rayVert)
     float px = XADD(r.ox, XMUL(t, r.dx)), py = XADD(r.oy, XMUL(t, r.dy)), pz = XADD(r.oz, XMUL(t, r.dz));
     float ex = XSUB(px, r.ox), ey = XSUB(py, r.oy), ez = XSUB(pz, r.oz);
@@ -330,14 +338,17 @@ SQT_HD void desc_step(const SceneView &sc, TravLane &L, Counters *cn) {
 // One triangle of the leaf (BIH.hs:105-109): V.mapMaybe over the leaf's triangles, minimumBy (comparing dist).
 // base-4.9 minimumBy = foldr1 min' with min' x y = GT -> y ; _ -> x : walk from the last triangle
 // to the first, the earlier one wins unless it is strictly farther.
-SQT_HD void tri_step(const SceneView &sc, TravLane &L) {
+template <bool COUNT>
+SQT_HD void tri_step(const SceneView &sc, TravLane &L, Counters *cn) {
     const uint32_t idx = L.child + (uint32_t)L.i;
     const float4 *p = sc.tris + 3 * (size_t)idx;
     const float4 a0 = SQT_LDG4(p), a1 = SQT_LDG4(p + 1), a2 = SQT_LDG4(p + 2);
     float t, dist;
-    if (moller_trumbore(a0, a1, a2, L.r, t, dist)) {
+    int stage;
+    if (moller_trumbore(a0, a1, a2, L.r, t, dist, stage)) {
         if (L.cur.tri < 0 || !cmp_gt(dist, L.cur.dist)) { L.cur.tri = (int)idx; L.cur.t = t; L.cur.dist = dist; }
     }
+    if (COUNT) { cn->mt_pass_a += stage >= 1; cn->mt_pass_u += stage >= 2; cn->mt_pass_v += stage >= 3; cn->mt_accept += stage >= 4; }
     if (--L.i < 0) L.state = ST_RET;
 }
 
@@ -379,7 +390,7 @@ SQT_HD Hit traverse(const SceneView &sc, const Ray &r, Counters *cn) {
         if (L.state == ST_RET) ret_step(sc, L);
         if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
         if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, cn);
-        if (L.state == ST_LEAF) tri_step(sc, L);
+        if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, cn);
     }
     return L.cur;
 }

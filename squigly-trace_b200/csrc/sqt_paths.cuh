@@ -319,7 +319,7 @@ SQT_HD_NOINLINE void run_lane(const SceneView &sc, Policy &pol, Counters *cn) {
         if (L.state == ST_RET) ret_step(sc, L);
         if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
         if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, cn);
-        if (L.state == ST_LEAF) tri_step(sc, L);
+        if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, cn);
     }
 }
 

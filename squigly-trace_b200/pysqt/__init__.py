@@ -67,7 +67,8 @@ class Stats(C.Structure):
     _fields_ = [("device_ms", C.c_double), ("primary_ms", C.c_double), ("paths_ms", C.c_double), ("tonemap_ms", C.c_double),
                 ("reduce_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("rays_traced", C.c_uint64),
                 ("rays_reference", C.c_uint64), ("samples", C.c_uint64), ("branch_visits", C.c_uint64),
-                ("child_box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("leaves_culled", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("child_box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("leaves_culled", C.c_uint64), ("mt_pass_a", C.c_uint64), ("mt_pass_u", C.c_uint64),
+                ("mt_pass_v", C.c_uint64), ("mt_accept", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):

@@ -48,7 +48,7 @@ void emu_set_leaf_cull(emu_scene *s, int on) { s->view.leaf_cull = on ? 1u : 0u;
 
 void emu_intersect_batch(emu_scene *s, const float *org, const float *dir, long long n, int *tri_out, float *dist_out,
                          float *point_out, unsigned long long *counters4 /* 5 values */) {
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {};
     PathStats st = {0, 0, 0};
     const long long n_lanes = 5;
     for (long long l = 0; l < n_lanes; ++l) { BatchPolicy pol(org, dir, n, l, n_lanes, tri_out, dist_out, point_out, st); run_lane<true>(s->view, pol, &cn); }
@@ -70,7 +70,7 @@ void emu_render(emu_scene *s, const sqt_camera *cam, const sqt_render_params *p,
     d.terminate_on_black = (s->lay.terminate_on_black_ok && !(p->flags & SQT_F_NO_EARLY_TERMINATION)) ? 1 : 0;
     const long long npix = (long long)d.rows * d.cols, nwork = work_items(d);
     std::memset(accum, 0, (size_t)npix * 12);
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {};
     PathStats st = {0, 0, 0};
     const long long n_lanes = 7;
     if (d.mode == 1) {
@@ -113,7 +113,7 @@ long long emu_trace_lane(emu_scene *s, const sqt_camera *cam, const sqt_render_p
     d.terminate_on_black = s->lay.terminate_on_black_ok;
     const long long npix = (long long)d.rows * d.cols;
     std::vector<int2> prim((size_t)npix);
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {};
     PathStats st = {0, 0, 0};
     for (long long w = w0; w < w1; ++w) {
         const Ray r = make_ray(d, (int)(w / d.cols), (int)(w % d.cols));
@@ -136,7 +136,7 @@ long long emu_trace_lane(emu_scene *s, const sqt_camera *cam, const sqt_render_p
             if (L.state == ST_DESC) desc_step<false>(s->view, L, &cn);
             if (n < cap) out[n] = 'T'; n++;
         } else if (L.state == ST_ENTER) { enter_step<false>(s->view, L, &cn); if (n < cap) out[n] = 'E'; n++; }
-        else if (L.state == ST_LEAF) { tri_step(s->view, L); if (n < cap) out[n] = 'L'; n++; }
+        else if (L.state == ST_LEAF) { tri_step<false>(s->view, L, &cn); if (n < cap) out[n] = 'L'; n++; }
     }
     return n < cap ? n : cap;
 }
@@ -148,7 +148,7 @@ void emu_leaf_cull_stats(emu_scene *s, const float *org, const float *dir, long 
     for (int k = 0; k < 6; ++k) out[k] = 0;
     const uint32_t saved_cull = s->view.leaf_cull;
     s->view.leaf_cull = 0;
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {};
     uint32_t stack[kStackWords];
     for (long long i = 0; i < n; ++i) {
         TravLane L; L.stack = stack;
@@ -179,7 +179,7 @@ void emu_leaf_cull_stats(emu_scene *s, const float *org, const float *dir, long 
                 const float d1 = std::fabs(L.r.dx) + std::fabs(L.r.dy) + std::fabs(L.r.dz);
                 const float m = margin * (s1 + E) * d1 * (1.0f + d1) * E2 + 1e-4f;
                 const bool box_hit = slab_exact(lo[0] - m, lo[1] - m, lo[2] - m, hi[0] + m, hi[1] + m, hi[2] + m, L.r, L.dfx, L.dfy, L.dfz);
-                while (L.state == ST_LEAF) tri_step(s->view, L);
+                while (L.state == ST_LEAF) tri_step<false>(s->view, L, &cn);
                 out[0] += 1; out[1] += count;
                 if (!box_hit) { out[2] += 1; out[3] += count; }
                 if (L.cur.tri >= 0) { out[4] += 1; if (!box_hit) out[5] += 1; }

@@ -1,0 +1,96 @@
+"""Kernel logic (csrc/sqt_core.cuh + sqt_paths.cuh compiled for the host, tests/emu) against the oracle.
+
+This is the same source the CUDA kernels instantiate, run lane by lane on the CPU, so traversal/integrator logic
+bugs are caught without a GPU.  The GPU parity tests proper are in test_gpu_parity.py.  CPU only."""
+import numpy as np
+import pytest
+
+import pysqt
+from oracle import oracle as O
+from pysqt import scenes
+from common import Emu, adversarial_rays, assert_same_hits, bits, build_pair, random_rays
+
+
+@pytest.fixture(scope="module")
+def emu(host_scene):
+    return Emu(host_scene)
+
+
+def test_primary_and_random_rays(emu, oracle_scene, camera):
+    org, dirs = O.make_rays(O.make_params(160, 160, 1), camera)
+    o2, d2 = random_rays(30000, 1)
+    org = np.concatenate([org, o2]); dirs = np.concatenate([dirs, d2])
+    want = oracle_scene.intersect_batch(org, dirs, counters=True)
+    emu.set_leaf_cull(False)
+    got = emu.intersect_batch(org, dirs)
+    emu.set_leaf_cull(True)
+    assert_same_hits(got, want, "emu, culling off")
+    assert got[3]["branch_visits"] == int(want[3][0]) and got[3]["tri_tests"] == int(want[3][3]) and got[3]["child_box_tests"] == int(want[3][1])
+    culled = emu.intersect_batch(org, dirs)
+    assert_same_hits(culled, want, "emu, culling on")
+    assert culled[3]["leaves_culled"] > 0 and culled[3]["tri_tests"] < got[3]["tri_tests"]
+
+
+def test_adversarial_rays(emu, oracle_scene):
+    v9, _ = oracle_scene.tris()
+    org, dirs = adversarial_rays(v9, n_each=512)
+    assert_same_hits(emu.intersect_batch(org, dirs), oracle_scene.intersect_batch(org, dirs), "adversarial")
+
+
+@pytest.mark.parametrize("gen,n", [("cornell", 4000), ("soup", 30000), ("mesh", 20000)])
+def test_synthetic_scenes(gen, n):
+    v9, mi, mats = {"cornell": scenes.cornell_box, "soup": scenes.triangle_soup, "mesh": scenes.subdivided_mesh}[gen](n)
+    osc, hs = build_pair(v9, mi, mats)
+    e = Emu(hs)
+    org, dirs = random_rays(20000, 2, lo=-1.5, hi=1.5)
+    assert_same_hits(e.intersect_batch(org, dirs), osc.intersect_batch(org, dirs), gen)
+
+
+@pytest.mark.parametrize("w,h,spp,depth,literal,flags", [
+    (64, 48, 6, 3, False, 0), (48, 48, 4, 8, False, 0), (56, 40, 3, 3, True, 0),
+    (48, 32, 4, 5, False, pysqt.SQT_F_NO_PRIMARY_REUSE | pysqt.SQT_F_NO_EARLY_TERMINATION), (32, 32, 2, 1, False, 0)])
+def test_render_bit_exact(emu, oracle_scene, camera, w, h, spp, depth, literal, flags):
+    got = emu.render(camera, pysqt.make_params(w, h, spp, max_depth=depth, seed=5, literal=literal, flags=flags))
+    ref = oracle_scene.render(camera, O.make_params(w, h, spp, max_depth=depth, seed=5, trig=1, literal=literal))
+    assert np.array_equal(bits(got["accum"]), bits(ref["accum"])) and np.array_equal(got["rgb8"], ref["rgb8"])
+    assert got["samples"] == ref["samples"]
+    if flags:
+        assert got["rays"] == ref["rays"]
+    else:
+        assert got["rays"] <= ref["rays"]
+
+
+def test_cast_mode(emu, oracle_scene, camera):
+    got = emu.render(camera, pysqt.make_params(64, 48, 3, mode=1))
+    ref = oracle_scene.render(camera, O.make_params(64, 48, 3, mode=1, trig=1))
+    assert np.array_equal(bits(got["accum"]), bits(ref["accum"])) and np.array_equal(got["rgb8"], ref["rgb8"])
+
+
+def test_rank_partition_sums_to_full_frame(emu, camera):
+    p = pysqt.make_params(72, 40, 3, max_depth=4, seed=2)
+    full = emu.render(camera, p)["accum"]
+    parts = [emu.render(camera, p, rank=r, world=4)["accum"] for r in range(4)]
+    assert np.array_equal(bits(sum(parts)), bits(full))
+    ps = pysqt.make_params(72, 40, 4, max_depth=4, seed=2, flags=pysqt.SQT_F_SPLIT_SAMPLES)
+    halves = [emu.render(camera, ps, rank=r, world=2)["accum"] for r in range(2)]
+    assert np.allclose(halves[0] + halves[1], emu.render(camera, pysqt.make_params(72, 40, 4, max_depth=4, seed=2))["accum"], rtol=1e-6, atol=1e-6)
+
+
+def test_upload_validation_errors(host_scene):
+    import ctypes as C
+    from common import emu_lib
+    E = emu_lib()
+
+    def err_of(desc):
+        h = E.emu_upload(C.byref(desc)); e = E.emu_error(h).decode(); E.emu_free(h); return e
+    d = host_scene.desc(); d.n_mats = 0
+    assert "no materials" in err_of(d)
+    nodes = host_scene.nodes.copy(); nodes["a"][0] = (nodes["a"][0] & 0xC0000000) | 0x3fffffff
+    d = host_scene.desc(); d.nodes = nodes.ctypes.data
+    assert "out of range" in err_of(d)
+    nodes = host_scene.nodes.copy(); nodes["b"][0] = 0          # right child = root: not a tree
+    d = host_scene.desc(); d.nodes = nodes.ctypes.data
+    assert "twice" in err_of(d)
+    tris = host_scene.tris.copy(); tris["material"][5] = 99
+    d = host_scene.desc(); d.tris = tris.ctypes.data
+    assert "material 99" in err_of(d)
