@@ -150,6 +150,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import pysqt
 
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -33,7 +33,8 @@ struct DeviceStats {
     unsigned long long rays, samples, primary_reused;
     unsigned long long branch_visits, child_box_tests, tri_tests, leaves_culled;
     unsigned long long mt_pass_a, mt_pass_u, mt_pass_v, mt_accept;
-    unsigned long long work_next;       // dynamic work counter of k_paths
+    unsigned long long n_hit;           // length of the pixel list k_primary builds
+    unsigned long long work_next[64];   // dynamic work counters of k_paths, one per round
 };
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -130,11 +131,26 @@ __global__ void __launch_bounds__(128) k_intersect_batch(SceneView sc, const flo
     flush_stats(ds, st, cn, COUNT);
 }
 
+struct DeviceAppend {
+    unsigned long long *counter;
+    int *list;
+    __device__ __forceinline__ void operator()(long long pixel) {
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned long long base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(counter, (unsigned long long)g.size());
+        base = g.shfl(base, 0);
+        list[base + g.thread_rank()] = (int)pixel;
+    }
+};
+
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_primary(SceneView sc, RenderParams p, int2 *__restrict__ prim, DeviceStats *ds, Tune tn) {
+__global__ void __launch_bounds__(128) k_primary(SceneView sc, RenderParams p, int2 *__restrict__ prim, int *__restrict__ pixel_list,
+                                                 DeviceStats *ds, Tune tn) {
     Counters cn = {};
     PathStats st = {0, 0, 0};
-    PrimaryPolicy pol(p, prim, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, st);
+    DeviceAppend app = {&ds->n_hit, pixel_list};
+    PrimaryPolicy<DeviceAppend> pol(p, prim, app, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                                    (long long)gridDim.x * blockDim.x, st);
     warp_loop<COUNT>(sc, pol, &cn, tn);
     flush_stats(ds, st, cn, COUNT);
 }
@@ -153,16 +169,25 @@ struct DeviceFetch {
     }
 };
 
+// One round of samples (sqt_paths.cuh): persistent lanes pull (pixel, sample) items from the round's counter.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, const int2 *__restrict__ prim,
-                                               float *__restrict__ accum, DeviceStats *ds, Tune tn) {
+__global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, Tune tn) {
     Counters cn = {};
     PathStats st = {0, 0, 0};
-    DeviceFetch fetch = {&ds->work_next, work_items(p)};
+    if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
+    DeviceFetch fetch = {&ds->work_next[round], rd.n_slots << rd.log2_s};
     uint16_t pm[SQT_MAX_DEPTH];
-    PathPolicy<DeviceFetch> pol(p, prim, accum, fetch, st, pm);
+    PathPolicy<DeviceFetch> pol(p, rd, fetch, st, pm);
     warp_loop<COUNT>(sc, pol, &cn, tn);
     flush_stats(ds, st, cn, COUNT);
+}
+
+// sum the round's samples into the per-pixel running sums, in sample order (Lib.hs:88)
+__global__ void __launch_bounds__(256) k_accumulate(RenderParams p, RoundInfo rd, float *__restrict__ accum, const DeviceStats *ds) {
+    if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < rd.n_slots; slot += stride)
+        accumulate_slot(p, rd, slot, accum);
 }
 
 template <bool COUNT>
@@ -265,6 +290,9 @@ struct sqt_ctx {
     // image buffers
     long long cap_pixels = 0;
     int2 *d_prim = nullptr;
+    int *d_pixel_list = nullptr;
+    float *d_sbuf = nullptr; long long cap_sbuf = 0;     // sample buffer of one round (bytes)
+    long long sbuf_budget = 2ll << 30;
     float *d_accum = nullptr;
     uint8_t *d_rgb8 = nullptr;
     long long img_pixels = 0;
@@ -320,6 +348,7 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
     for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
     CU(cudaMalloc(&c->d_stats, sizeof(DeviceStats)));
     CU(cudaMallocHost(&c->h_stats, sizeof(DeviceStats)));
+    if (const char *t = getenv("SQT_SBUF_MB")) { long long mb = atoll(t); if (mb > 0) c->sbuf_budget = mb << 20; }
     if (const char *t = getenv("SQT_TUNE")) {        // "a_leave,b_leave,c_min" -- scheduling knobs only, results do not depend on them
         int a, b, cm;
         if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->tune = {a, b, cm};
@@ -338,7 +367,7 @@ extern "C" int sqt_destroy(sqt_ctx *c) {
     cudaSetDevice(c->device);
     if (c->comm && nccl_api()->lib) nccl_api()->CommDestroy(c->comm);
     free_scene(c);
-    cudaFree(c->d_prim); cudaFree(c->d_accum); cudaFree(c->d_rgb8); cudaFree(c->d_stats);
+    cudaFree(c->d_prim); cudaFree(c->d_accum); cudaFree(c->d_rgb8); cudaFree(c->d_stats); cudaFree(c->d_pixel_list); cudaFree(c->d_sbuf);
     cudaFree(c->d_org); cudaFree(c->d_dir); cudaFree(c->d_dist); cudaFree(c->d_point); cudaFree(c->d_tri);
     cudaFreeHost(c->h_stats); cudaFreeHost(c->h_rgb8); cudaFreeHost(c->h_accum);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -401,12 +430,20 @@ extern "C" int sqt_set_option(sqt_ctx *ctx, int option, int value) {
 // ------------------------------------------------------------------------------ helpers
 static int ensure_image(sqt_ctx *ctx, long long npix) {
     if (npix <= ctx->cap_pixels) return SQT_OK;
-    cudaFree(ctx->d_prim); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgb8);
-    ctx->d_prim = nullptr; ctx->d_accum = nullptr; ctx->d_rgb8 = nullptr; ctx->cap_pixels = 0;
+    cudaFree(ctx->d_prim); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgb8); cudaFree(ctx->d_pixel_list);
+    ctx->d_prim = nullptr; ctx->d_accum = nullptr; ctx->d_rgb8 = nullptr; ctx->d_pixel_list = nullptr; ctx->cap_pixels = 0;
     CU(cudaMalloc(&ctx->d_prim, (size_t)npix * sizeof(int2)));
+    CU(cudaMalloc(&ctx->d_pixel_list, (size_t)(npix + 32) * sizeof(int)));
     CU(cudaMalloc(&ctx->d_accum, (size_t)npix * 3 * sizeof(float)));
     CU(cudaMalloc(&ctx->d_rgb8, (size_t)npix * 3));
     ctx->cap_pixels = npix;
+    return SQT_OK;
+}
+static int ensure_sbuf(sqt_ctx *ctx, long long bytes) {
+    if (bytes <= ctx->cap_sbuf) return SQT_OK;
+    cudaFree(ctx->d_sbuf); ctx->d_sbuf = nullptr; ctx->cap_sbuf = 0;
+    CU(cudaMalloc(&ctx->d_sbuf, (size_t)bytes));
+    ctx->cap_sbuf = bytes;
     return SQT_OK;
 }
 static int ensure_host_image(sqt_ctx *ctx, long long npix) {
@@ -526,16 +563,35 @@ static int enqueue_render(sqt_ctx *ctx, const RenderParams &d, bool count, uint3
         CU(cudaGetLastError()); nl++;
     } else {
         if (d.primary_reuse) {
-            if (count) k_primary<true><<<persistent_grid(ctx, k_primary<true>, nwork), 128, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_stats, ctx->tune);
-            else k_primary<false><<<persistent_grid(ctx, k_primary<false>, nwork), 128, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_stats, ctx->tune);
+            if (count) k_primary<true><<<persistent_grid(ctx, k_primary<true>, nwork), 128, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_pixel_list, ctx->d_stats, ctx->tune);
+            else k_primary<false><<<persistent_grid(ctx, k_primary<false>, nwork), 128, 0, st>>>(ctx->sc, d, ctx->d_prim, ctx->d_pixel_list, ctx->d_stats, ctx->tune);
             CU(cudaGetLastError()); nl++;
         }
         CU(cudaEventRecord(ctx->ev[1], st));
-        // persistent lanes: as many CTAs as stay resident, all of them pulling pixels from one counter
-        const int2 *prim = d.primary_reuse ? ctx->d_prim : nullptr;
-        if (count) k_paths<true><<<persistent_grid(ctx, k_paths<true>, nwork), 128, 0, st>>>(ctx->sc, d, prim, ctx->d_accum, ctx->d_stats, ctx->tune);
-        else k_paths<false><<<persistent_grid(ctx, k_paths<false>, nwork), 128, 0, st>>>(ctx->sc, d, prim, ctx->d_accum, ctx->d_stats, ctx->tune);
-        CU(cudaGetLastError()); nl++;
+        // rounds of S samples per pixel: trace (persistent lanes, one counter per round), then add in sample order
+        int k0, k1;
+        sample_range(d, k0, k1);
+        RoundInfo rd = {};
+        rd.pixel_list = d.primary_reuse ? ctx->d_pixel_list : nullptr;
+        rd.prim = d.primary_reuse ? ctx->d_prim : nullptr;
+        rd.n_slots = nwork; rd.slot_stride = nwork;
+        rd.log2_s = round_log2_s(nwork, k1 - k0 > 0 ? k1 - k0 : 1, ctx->sbuf_budget);
+        const int S = 1 << rd.log2_s;
+        if ((k1 - k0 + S - 1) / S > 64) return fail(ctx, SQT_E_UNSUPPORTED, "more than 64 sample rounds (raise SQT_SBUF_MB)");
+        const long long sbytes = nwork * (long long)S * 12ll;
+        rc = ensure_sbuf(ctx, sbytes); if (rc) return rc;
+        rd.sbuf = ctx->d_sbuf;
+        const int agrid = (int)((nwork + 255) / 256 < (long long)ctx->sm_count * 8 ? (nwork + 255) / 256 : (long long)ctx->sm_count * 8);
+        int round = 0;
+        for (int kb = k0; kb < k1; kb += S, ++round) {
+            rd.k0 = kb; rd.k1 = kb + S < k1 ? kb + S : k1;
+            CU(cudaMemsetAsync(ctx->d_sbuf, 0, (size_t)(nwork * (long long)(rd.k1 - rd.k0) * 12ll), st));
+            if (count) k_paths<true><<<persistent_grid(ctx, k_paths<true>, nwork << rd.log2_s), 128, 0, st>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->tune);
+            else k_paths<false><<<persistent_grid(ctx, k_paths<false>, nwork << rd.log2_s), 128, 0, st>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->tune);
+            CU(cudaGetLastError()); nl++;
+            k_accumulate<<<agrid > 0 ? agrid : 1, 256, 0, st>>>(d, rd, ctx->d_accum, ctx->d_stats);
+            CU(cudaGetLastError()); nl++;
+        }
     }
     CU(cudaEventRecord(ctx->ev[2], st));
     if (ctx->world > 1 && ctx->comm) {

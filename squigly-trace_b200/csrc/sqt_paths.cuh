@@ -62,33 +62,43 @@ SQT_HD void fold_path(const SceneView &sc, const uint16_t *pm, int last, float &
 }
 
 // ------------------------------------------------------------------------------- raytrace policy
-// Fetch: functor returning the next work item (>= 0) or -1 when the queue is empty.
+// Work item = one SAMPLE of one pixel (Lib.hs:84: `raytrace r scene ray 0` for generator r).  The samples of a
+// frame are rendered in rounds of `S` (a power of two) samples per pixel; within a round, item w is sample
+// k0 + (w mod S) of the pixel in slot (w div S) of the round's pixel list.  A path's radiance goes to a sample
+// buffer (ks-major: [ks][slot][3]); `accumulate_slot` then adds the S values of a pixel to its running sum in
+// sample order, continuing from the previous round -- so the per-pixel sum is the reference's sequential
+// `sum = foldl (+) 0` (Lib.hs:88) although the samples of a pixel are traced by different lanes.
+struct RoundInfo {
+    const int *pixel_list;     // slot -> pixel (hit pixels from k_primary), or nullptr: slot -> work_to_pixel(slot)
+    const int2 *prim;          // per pixel (tri, t bits) of the primary hit, or nullptr when primary reuse is off
+    float *sbuf;               // sample buffer of this round, zero-filled
+    long long n_slots;         // slots in use
+    long long slot_stride;     // allocation stride of one ks plane (>= n_slots)
+    int log2_s;                // S = 1 << log2_s
+    int k0, k1;                // samples [k0, k1) of this round, k1 - k0 <= S
+};
+
 template <class Fetch>
 struct PathPolicy {
     const RenderParams &p;
-    const int2 *prim;          // per pixel (tri, t bits) of the primary hit, or nullptr when primary reuse is off
-    float *accum;
+    const RoundInfo &rd;
     Fetch &fetch;
     PathStats &st;
     // per-lane path state
-    long long pixel = -1;
-    int k = 0, k0 = 0, k1 = 0, j = 0;        // sample index / range, bounce index of the hit being shaded
-    int ptri = -1; float pt = 0.0f;          // cached primary hit of the current pixel
-    int px = 0, py = 0;
-    unsigned long long rix = 0ull;
-    float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+    long long sidx = 0;                      // index of the current sample in sbuf (without the *3)
+    int j = 0;                               // bounce index of the hit being shaded
+    unsigned long long stream = 0ull;        // generator seed of the current sample: spp*(x + y*w) + k
     float saved_r = 0.0f; int saved_j = -1;  // draw j+1 of a scatter is draw j of the next bounce
-    bool any_emit = false, in_flight = false, need_pixel = true;
+    bool any_emit = false, in_flight = false;
     uint16_t *pm;                            // SQT_MAX_DEPTH entries of lane-private memory: material of every
                                              // shaded bounce of the current path
 
-    SQT_HD PathPolicy(const RenderParams &p_, const int2 *prim_, float *accum_, Fetch &f_, PathStats &st_, uint16_t *pm_)
-        : p(p_), prim(prim_), accum(accum_), fetch(f_), st(st_), pm(pm_) { sample_range(p, k0, k1); }
+    SQT_HD PathPolicy(const RenderParams &p_, const RoundInfo &rd_, Fetch &f_, PathStats &st_, uint16_t *pm_)
+        : p(p_), rd(rd_), fetch(f_), st(st_), pm(pm_) {}
 
     SQT_HD float draw_r(uint32_t jj) {
         if ((int)jj == saved_j) return saved_r;
         uint32_t w[4];
-        const unsigned long long stream = rix + (unsigned long long)k;
         philox4x32_10((uint32_t)stream, (uint32_t)(stream >> 32), jj >> 2, 0x52545153u, (uint32_t)p.seed,
                       (uint32_t)(p.seed >> 32), w);
         const uint32_t q = jj & 3u;
@@ -97,7 +107,7 @@ struct PathPolicy {
 
     template <bool COUNT>
     SQT_HD void regen(const SceneView &sc, TravLane &L, Counters *cn) {
-        bool path_over = false, start = false;
+        bool path_over = false;
         int htri = -1; float ht = 0.0f;
         if (in_flight) {                                  // the ray of Lib.hs:131 came back
             in_flight = false;
@@ -107,48 +117,41 @@ struct PathPolicy {
         }
         for (;;) {
             if (path_over) {
-                // ---- finish sample k: add its radiance, in sample order (Lib.hs:87-88)
+                // ---- the sample is finished: store its radiance (samples that never met an emitter are exactly +0,
+                //      which the zero-filled buffer already holds)
                 if (any_emit) {
                     float lr, lg, lb;
                     fold_path(sc, pm, j, lr, lg, lb);
-                    sr = XADD(sr, lr); sg = XADD(sg, lg); sb = XADD(sb, lb);
-                }   // else the sample is exactly (+0,+0,+0) and sum + 0 == sum
+                    rd.sbuf[3 * sidx] = lr; rd.sbuf[3 * sidx + 1] = lg; rd.sbuf[3 * sidx + 2] = lb;
+                }
                 st.samples += 1;
                 path_over = false;
-                if (++k == k1) {
-                    accum[3 * pixel] = sr; accum[3 * pixel + 1] = sg; accum[3 * pixel + 2] = sb;
-                    need_pixel = true;
-                } else start = true;
+                htri = -1;
             }
-            if (need_pixel) {
+            if (htri < 0) {
+                // ---- next sample
                 const long long w = fetch();
                 if (w < 0) { L.state = ST_EXIT; return; }
-                pixel = work_to_pixel(p, w);
-                if (pixel < 0 || k0 >= k1) continue;
-                py = (int)(pixel / p.cols); px = (int)(pixel % p.cols);
-                rix = (unsigned long long)p.spp * ((unsigned long long)px + (unsigned long long)py * (unsigned long long)p.seed_stride);
-                sr = sg = sb = 0.0f;
-                k = k0;
-                if (prim) {
-                    const int2 ph = prim[pixel];
-                    ptri = ph.x; pt = u2f((uint32_t)ph.y);
-                    if (ptri < 0) {                       // every sample of this pixel is black (accum pre-zeroed)
-                        st.samples += (unsigned long long)(k1 - k0);
-                        st.primary_reused += (unsigned long long)(k1 - k0);
-                        continue;
-                    }
-                }
-                need_pixel = false;
-                start = true;
-            }
-            if (start) {
-                // A sample begins at the cached primary hit (bounce 0 already intersected: the primary ray is
-                // the same for every sample of a pixel, Lib.hs:81) or, with primary reuse off, by tracing the
-                // primary ray again like Lib.hs:84 does.
-                start = false; any_emit = false; saved_j = -1;
+                const long long slot = w >> rd.log2_s;
+                const int ks = (int)(w & ((1ll << rd.log2_s) - 1));
+                const int k = rd.k0 + ks;
+                if (k >= rd.k1) continue;
+                const long long pixel = rd.pixel_list ? (long long)rd.pixel_list[slot] : work_to_pixel(p, slot);
+                if (pixel < 0) continue;
+                const int py = (int)(pixel / p.cols), px = (int)(pixel % p.cols);
+                stream = (unsigned long long)p.spp * ((unsigned long long)px + (unsigned long long)py * (unsigned long long)p.seed_stride)
+                         + (unsigned long long)k;
+                sidx = (long long)ks * rd.slot_stride + slot;
+                any_emit = false; saved_j = -1;
                 L.r = make_ray(p, py, px);
-                if (prim) { htri = ptri; ht = pt; j = 0; st.primary_reused += 1; }
-                else { j = -1; in_flight = true; start_ray<COUNT>(sc, L, cn); return; }
+                if (rd.prim) {
+                    // the primary ray is the same for every sample of a pixel (Lib.hs:81): its hit was traced once
+                    const int2 ph = rd.prim[pixel];
+                    htri = ph.x; ht = u2f((uint32_t)ph.y); j = 0;
+                    st.primary_reused += 1;
+                } else {                                  // primary reuse off: trace it again like Lib.hs:84 does
+                    j = -1; in_flight = true; start_ray<COUNT>(sc, L, cn); return;
+                }
             }
             // ---- shade the hit of bounce j (raytrace, Lib.hs:127-137); L.r is the ray that produced it
             const float4 *tp = sc.tris + 3 * (size_t)htri;
@@ -172,6 +175,27 @@ struct PathPolicy {
         }
     }
 };
+
+// avg-in-order part of renderPixel (Lib.hs:87-88): add the round's samples of one slot to the pixel's running sum,
+// strictly in sample order.
+SQT_HD void accumulate_slot(const RenderParams &p, const RoundInfo &rd, long long slot, float *accum) {
+    const long long pixel = rd.pixel_list ? (long long)rd.pixel_list[slot] : work_to_pixel(p, slot);
+    if (pixel < 0) return;
+    float sr = accum[3 * pixel], sg = accum[3 * pixel + 1], sb = accum[3 * pixel + 2];
+    const int n = rd.k1 - rd.k0;
+    for (int ks = 0; ks < n; ++ks) {
+        const long long i = 3 * ((long long)ks * rd.slot_stride + slot);
+        sr = XADD(sr, rd.sbuf[i]); sg = XADD(sg, rd.sbuf[i + 1]); sb = XADD(sb, rd.sbuf[i + 2]);
+    }
+    accum[3 * pixel] = sr; accum[3 * pixel + 1] = sg; accum[3 * pixel + 2] = sb;
+}
+
+// samples per pixel per round: the largest power of two <= spp whose sample buffer (slots * S * 12 B) fits the budget
+SQT_HD int round_log2_s(long long slots, int n_samples, long long budget_bytes) {
+    int l = 0;
+    while ((1 << (l + 1)) <= n_samples && slots * (long long)(1 << (l + 1)) * 12ll <= budget_bytes) ++l;
+    return l;
+}
 
 // ------------------------------------------------------------------------------- batched intersect policy
 // Scene.intersect over a ray batch (Geometry.hs:64): lane takes rays idx, idx + stride, ...
@@ -210,14 +234,16 @@ struct BatchPolicy {
 
 // ------------------------------------------------------------------------------- primary-hit policy
 // makeRay (Lib.hs:107-114) + closest hit for every owned pixel, cached as (tri, t bits)
+template <class Append>
 struct PrimaryPolicy {
     const RenderParams &p;
     int2 *prim;
+    Append &append;            // functor: append(pixel) adds a pixel whose primary ray hit something to the pixel list
     long long nwork, w, stride, pixel = -1;
     PathStats &st;
     bool in_flight = false;
-    SQT_HD PrimaryPolicy(const RenderParams &p_, int2 *prim_, long long nwork_, long long first, long long stride_, PathStats &st_)
-        : p(p_), prim(prim_), nwork(nwork_), w(first), stride(stride_), st(st_) {}
+    SQT_HD PrimaryPolicy(const RenderParams &p_, int2 *prim_, Append &app_, long long nwork_, long long first, long long stride_, PathStats &st_)
+        : p(p_), prim(prim_), append(app_), nwork(nwork_), w(first), stride(stride_), st(st_) {}
 
     template <bool COUNT>
     SQT_HD void regen(const SceneView &sc, TravLane &L, Counters *cn) {
@@ -226,6 +252,12 @@ struct PrimaryPolicy {
             st.rays += 1;
             int2 h; h.x = L.cur.tri; h.y = (int)f2u(L.cur.t);
             prim[pixel] = h;
+            if (L.cur.tri >= 0) append(pixel);
+            else {                                        // every sample of this pixel is black (Lib.hs:130): nothing to trace
+                int k0, k1;
+                sample_range(p, k0, k1);
+                if (k1 > k0) { st.samples += (unsigned long long)(k1 - k0); st.primary_reused += (unsigned long long)(k1 - k0); }
+            }
             w += stride;
         }
         for (;;) {

@@ -20,6 +20,13 @@ struct emu_scene {
     std::string err;
 };
 
+static long long sbuf_budget = 1ll << 20;      // small on purpose: forces several sample rounds in the tests
+
+struct VecAppend {
+    std::vector<int> *v;
+    void operator()(long long pixel) { v->push_back((int)pixel); }
+};
+
 struct SeqFetch {
     long long next, n;
     long long operator()() { return next < n ? next++ : -1; }
@@ -45,6 +52,7 @@ const char *emu_error(emu_scene *s) { return s->err.c_str(); }
 void emu_free(emu_scene *s) { delete s; }
 int emu_height(emu_scene *s) { return (int)s->lay.height; }
 void emu_set_leaf_cull(emu_scene *s, int on) { s->view.leaf_cull = on ? 1u : 0u; }
+void emu_set_sbuf_budget(long long bytes) { sbuf_budget = bytes; }
 
 void emu_intersect_batch(emu_scene *s, const float *org, const float *dir, long long n, int *tri_out, float *dist_out,
                          float *point_out, unsigned long long *counters4 /* 5 values */) {
@@ -77,18 +85,38 @@ void emu_render(emu_scene *s, const sqt_camera *cam, const sqt_render_params *p,
         for (long long l = 0; l < n_lanes; ++l) { CastPolicy pol(d, accum, nwork, l, n_lanes, st); run_lane<true>(s->view, pol, &cn); }
     } else {
         std::vector<int2> prim;
+        std::vector<int> pixel_list;
         if (d.primary_reuse) {
             prim.resize((size_t)npix);
-            for (long long l = 0; l < n_lanes; ++l) { PrimaryPolicy pol(d, prim.data(), nwork, l, n_lanes, st); run_lane<true>(s->view, pol, &cn); }
+            VecAppend app{&pixel_list};
+            // lanes interleave like the device's grid-stride lanes; the resulting list order is arbitrary on the device too
+            for (long long l = n_lanes - 1; l >= 0; --l) { PrimaryPolicy<VecAppend> pol(d, prim.data(), app, nwork, l, n_lanes, st); run_lane<true>(s->view, pol, &cn); }
         }
-        SeqFetch fetch{0, nwork};
+        int k0, k1;
+        sample_range(d, k0, k1);
+        RoundInfo rd = {};
+        rd.pixel_list = d.primary_reuse ? pixel_list.data() : nullptr;
+        rd.prim = d.primary_reuse ? prim.data() : nullptr;
+        rd.n_slots = d.primary_reuse ? (long long)pixel_list.size() : nwork;
+        rd.slot_stride = nwork;
+        rd.log2_s = round_log2_s(nwork, k1 - k0 > 0 ? k1 - k0 : 1, sbuf_budget);
+        const int S = 1 << rd.log2_s;
+        std::vector<float> sbuf((size_t)(nwork * S * 3 + 3));
+        rd.sbuf = sbuf.data();
         uint16_t pm[SQT_MAX_DEPTH];
-        for (long long l = 0; l < n_lanes; ++l) {
-            // each lane drains what is left of the queue after taking a few items, like lanes racing on the counter
-            SeqFetch part{fetch.next, l + 1 == n_lanes ? nwork : std::min(nwork, fetch.next + (nwork + n_lanes - 1) / n_lanes)};
-            PathPolicy<SeqFetch> pol(d, d.primary_reuse ? prim.data() : nullptr, accum, part, st, pm);
-            run_lane<true>(s->view, pol, &cn);
-            fetch.next = part.n;
+        for (int kb = k0; kb < k1; kb += S) {
+            rd.k0 = kb; rd.k1 = kb + S < k1 ? kb + S : k1;
+            std::fill(sbuf.begin(), sbuf.end(), 0.0f);
+            const long long items = rd.n_slots << rd.log2_s;
+            SeqFetch fetch{0, items};
+            for (long long l = 0; l < n_lanes; ++l) {
+                // every lane takes a contiguous share of the queue, like lanes racing on the device's counter
+                SeqFetch part{fetch.next, l + 1 == n_lanes ? items : std::min(items, fetch.next + (items + n_lanes - 1) / n_lanes)};
+                PathPolicy<SeqFetch> pol(d, rd, part, st, pm);
+                run_lane<true>(s->view, pol, &cn);
+                fetch.next = part.n;
+            }
+            for (long long slot = 0; slot < rd.n_slots; ++slot) accumulate_slot(d, rd, slot, accum);
         }
     }
     if (rgb8) {
@@ -120,10 +148,18 @@ long long emu_trace_lane(emu_scene *s, const sqt_camera *cam, const sqt_render_p
         const Hit h = traverse<false>(s->view, r, &cn);
         prim[(size_t)w].x = h.tri; prim[(size_t)w].y = (int)f2u(h.t);
     }
-    std::vector<float> accum((size_t)npix * 3);
-    SeqFetch fetch{w0, w1};
+    // the lane traces all samples of the pixels [w0, w1) whose primary ray hits, one after the other
+    std::vector<int> pixel_list;
+    for (long long w = w0; w < w1; ++w) if (prim[(size_t)w].x >= 0) pixel_list.push_back((int)w);
+    RoundInfo rd = {};
+    rd.pixel_list = pixel_list.data(); rd.prim = prim.data(); rd.n_slots = (long long)pixel_list.size(); rd.slot_stride = rd.n_slots;
+    rd.log2_s = 0; while ((1 << rd.log2_s) < d.spp) ++rd.log2_s;
+    rd.k0 = 0; rd.k1 = d.spp;
+    std::vector<float> sbuf((size_t)(rd.n_slots << rd.log2_s) * 3 + 3);
+    rd.sbuf = sbuf.data();
+    SeqFetch fetch{0, rd.n_slots << rd.log2_s};
     uint16_t pm[SQT_MAX_DEPTH];
-    PathPolicy<SeqFetch> pol(d, prim.data(), accum.data(), fetch, st, pm);
+    PathPolicy<SeqFetch> pol(d, rd, fetch, st, pm);
     uint32_t stack[kStackWords];
     TravLane L;
     L.stack = stack; L.state = ST_DONE; L.sp = 0; L.cur.tri = -1;

@@ -232,7 +232,25 @@ def test_resident_then_download_equals_render(gpu_ctx, host_scene, camera):
     st = gpu_ctx.render_resident(camera, p)
     rgb8, accum = gpu_ctx.download(p.rows, p.cols)
     assert np.array_equal(a["rgb8"], rgb8) and np.array_equal(bits(a["accum"]), bits(accum))
-    assert st["rays_traced"] == a["stats"]["rays_traced"] and st["kernel_launches"] == 3
+    # k_primary + one (k_paths, k_accumulate) pair per sample round + k_tonemap
+    assert st["rays_traced"] == a["stats"]["rays_traced"] and st["kernel_launches"] == 4
+
+
+def test_many_sample_rounds_are_bit_identical(host_scene, camera, monkeypatch):
+    """A tiny sample-buffer budget forces several rounds of samples; the per-pixel sums must not change."""
+    monkeypatch.setenv("SQT_SBUF_MB", "1")
+    small = pysqt.Context(0)
+    small.upload(host_scene)
+    p = pysqt.make_params(160, 120, 24, max_depth=4, seed=8)
+    a = small.render(camera, p)
+    small.close()
+    monkeypatch.delenv("SQT_SBUF_MB")
+    big = pysqt.Context(0)
+    big.upload(host_scene)
+    b = big.render(camera, p)
+    big.close()
+    assert a["stats"]["kernel_launches"] > b["stats"]["kernel_launches"]
+    assert np.array_equal(bits(a["accum"]), bits(b["accum"])) and np.array_equal(a["rgb8"], b["rgb8"])
 
 
 def test_render_is_deterministic_and_seed_sensitive(gpu_ctx, host_scene, camera):
