@@ -95,15 +95,18 @@ __device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Coun
         //      The few stragglers left over keep their state and continue next round.
         for (;;) {
             const unsigned mt = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET);
-            const unsigned me = __ballot_sync(FULL, L.state == ST_ENTER);
-            const unsigned ml = __ballot_sync(FULL, L.state == ST_LEAF);
-            if (__popc(mt) > tn.a_leave || (mt != 0u && (me | ml) == 0u)) {
+            if (__popc(mt) > tn.a_leave) {
                 if (L.state == ST_RET) ret_step(sc, L);
                 if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
                 continue;
             }
-            if (me != 0u) {
+            if (__any_sync(FULL, L.state == ST_ENTER)) {
                 if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, cn);
+                continue;
+            }
+            if (mt != 0u && !__any_sync(FULL, L.state == ST_LEAF)) {      // only stragglers are left and nobody has triangles
+                if (L.state == ST_RET) ret_step(sc, L);
+                if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
                 continue;
             }
             break;
@@ -305,7 +308,7 @@ struct sqt_ctx {
     int *d_tri = nullptr;
     // pinned host staging for image I/O
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
-    Tune tune = {8, 1, 4};
+    Tune tune = {8, 1, 8};
     // group
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
