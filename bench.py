@@ -34,6 +34,7 @@ for p in (ROOT, PKG):
 WIDTH, HEIGHT, SPP, DEPTH, SEED = 1920, 1080, 1024, 8, 0
 DATA = os.path.join(ROOT, "data")
 WORKLOAD = "data/scene.obj 1920x1080 1024spp depth8"
+NCU_DRAM_BYTES_PER_LAUNCH = 193057536 + 169222400      # profiles/r01_k_paths_v3_rounds.txt
 
 
 class ClockSampler:
@@ -150,7 +151,11 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import pysqt
 
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
+    # NCCL prints its version banner with printf on stdout when NCCL_DEBUG is set in the environment: keep fd 1
+    # pointed at stderr until the one JSON line is ready.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -252,10 +257,13 @@ def run_ours(args, rank, world, local_rank):
         mem_bytes = 16 * ref_cnt["branch_visits"] + 36 * ref_cnt["tri_tests"]
         keys = ("rays_traced", "branch_visits", "child_box_tests", "tri_tests", "mt_pass_a", "mt_pass_u", "mt_pass_v", "mt_accept", "leaves_culled")
         roof = {"bound": "fp32", "kernel": "k_paths", "achieved": achieved, "peak": fp32_peak / 1e3, "unit": "TFLOP/s",
-                "frac": achieved / (fp32_peak / 1e3), "traffic": None,
+                "frac": achieved / (fp32_peak / 1e3), "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 64-spp k_paths launch (the bench issues 16 such "
+                                  "launches per frame), ncu --set full, profiles/r01_k_paths_v3_rounds.txt",
                 "peak_source": "measured live: non-fused FADD/FMUL issue rate of this GPU (sqt_measure_fp32_peak); FMA contraction is "
                                "forbidden on the bit-exact path, so this is the FP32 ceiling (MEASURED_PEAKS.json has no FP32 figure)",
-                "kernel_ms": k_ms, "kernel_share_of_step": paths_ms / dev_ms,
+                "kernel_ms": k_ms, "kernel_ms_note": "all k_paths + k_accumulate launches of one frame (one pair per 64-spp round)",
+                "kernel_share_of_step": paths_ms / dev_ms,
                 "algorithmic": dict({k: ref_cnt[k] for k in keys}, fp32_ops=ops, fp32_ops_upper=algorithmic_fp32_ops_upper(ref_cnt),
                                     node_tri_bytes=mem_bytes, note="reference algorithm, guard-aware (SURVEY 8d)"),
                 "executed": dict({k: exe_cnt[k] for k in keys}, fp32_ops=algorithmic_fp32_ops(exe_cnt),
@@ -267,6 +275,8 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         print(json.dumps({
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -56,21 +56,21 @@ def cornell_box(target_tris=10000, seed=0x5171):
 
 
 def subdivided_mesh(target_tris=1_000_000, seed=0x5172):
-    """Config 4: a jittered height-field mesh (deep BIH, traversal bound) over x,z... in [-2,2]^2 with an
-    emissive quad above it and diffuse material."""
+    """Config 4: a jittered height-field mesh (deep BIH, traversal bound) standing like a back wall: x, z in [-2,2],
+    y = -1 + relief, facing the camera of data/camera (at y = 7 looking down -y); one emissive quad above, diffuse."""
     rng = np.random.default_rng(seed)
     n = max(2, int(round(np.sqrt(target_tris / 2.0))))
-    xs = np.linspace(-2, 2, n + 1); ys = np.linspace(-2, 2, n + 1)
-    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    xs = np.linspace(-2, 2, n + 1); zs = np.linspace(-2, 2, n + 1)
+    X, Z = np.meshgrid(xs, zs, indexing="ij")
     edge = 4.0 / n
-    Z = (-1.0 + 0.35 * np.sin(2.3 * X) * np.cos(1.7 * Y) + 0.15 * np.sin(9.1 * X + 1.0) * np.sin(7.7 * Y)
+    Y = (-1.0 + 0.35 * np.sin(2.3 * X) * np.cos(1.7 * Z) + 0.15 * np.sin(9.1 * X + 1.0) * np.sin(7.7 * Z)
          + rng.uniform(-1e-3, 1e-3, X.shape) * edge)
     X = X + rng.uniform(-1e-3, 1e-3, X.shape) * edge
-    Y = Y + rng.uniform(-1e-3, 1e-3, X.shape) * edge
+    Z = Z + rng.uniform(-1e-3, 1e-3, X.shape) * edge
     P = np.stack([X, Y, Z], -1)
     a, b, c, d = P[:-1, :-1], P[1:, :-1], P[1:, 1:], P[:-1, 1:]
     tris = np.concatenate([np.concatenate([a, b, c], -1).reshape(-1, 9), np.concatenate([a, c, d], -1).reshape(-1, 9)])
-    light = _quad_grid([-0.7, -0.7, 1.9], [1.4, 0, 0], [0, 1.4, 0], 1, 1)
+    light = _quad_grid([-0.7, 0.2, 1.95], [1.4, 0, 0], [0, 1.4, 0], 1, 1)
     v9 = np.concatenate([tris.astype(np.float32), light])
     mi = np.concatenate([np.zeros(len(tris), np.int32), np.ones(len(light), np.int32)])
     mats = np.array([[0.0, 0.7, 0.7, 0.7, 0, 0, 0, 0], [0.0, 0, 0, 0, 100, 1, 1, 1]], np.float32)
@@ -93,6 +93,3 @@ def triangle_soup(n_tris=10_000_000, seed=0x5173, all_reflective=True):
     return v9, mi, mats
 
 
-def soup_camera():
-    """Camera for the synthetic scenes: same pose convention as data/camera (position + rotMatrixRads output)."""
-    return None
