@@ -185,6 +185,170 @@ __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, Rou
     flush_stats(ds, st, cn, COUNT);
 }
 
+// ------------------------------------------------------------------------------ ray pools
+// k_paths_pool: the same per-ray logic as k_paths, scheduled differently.  Every warp owns a POOL of P = 32*K rays
+// whose state lives in shared memory (structure of arrays, 24 words per ray; traversal stacks and per-path material
+// lists in global memory, one region per pool slot).  Each round the warp counts how many of its rays wait for a
+// traversal step, a leaf entry, a triangle test or regeneration, picks the kind with the most waiting rays, gathers
+// up to 32 of them onto its lanes (rank by ballot, scatter slot ids through shared memory), runs a short burst of
+// that one kind of step with (nearly) all lanes active, and writes the rays back.  With one ray per lane at most
+// ~10 of 32 lanes share a step kind at any time (tools/sched_sim.py); regrouping rays lifts that limit.
+struct PoolTune { int burst_t, burst_l, c_min; };
+
+enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_META, PF_I, PF_CTRI, PF_CT, PF_CDIST,
+       PF_SP, PF_FLAGS, PF_DFAC, PF_WORDS };      // 18 words = 72 B per ray in shared memory
+// the integrator state of a slot (PathRay) is only touched by regeneration: 8 words per slot in global memory
+
+template <bool COUNT, int K>
+__global__ void __launch_bounds__(128) k_paths_pool(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, PoolTune tn,
+                                                    uint32_t *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath) {
+    extern __shared__ uint32_t pool_smem[];
+    constexpr int P = 32 * K;
+    const unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *pool = pool_smem + warp * (P * PF_WORDS + 32);
+    uint32_t *sel = pool + P * PF_WORDS;
+    const long long gslot0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * P;
+#define PW(f, slot) pool[(f) * P + (slot)]
+    Counters cn = {};
+    PathStats st = {0, 0, 0};
+    if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
+    DeviceFetch fetch = {&ds->work_next[round], rd.n_slots << rd.log2_s};
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int slot = lane + 32 * k;
+        PW(PF_FLAGS, slot) = (uint32_t)ST_DONE;
+        PW(PF_SP, slot) = 0u; PW(PF_CTRI, slot) = 0xffffffffu;
+        gpath[2 * (gslot0 + slot)] = make_uint4(0u, 0u, 0u, 0u);
+        gpath[2 * (gslot0 + slot) + 1] = make_uint4(0u, 0u, 0u, 0u);      // saved_j = -1 (stored +1), any_emit = in_flight = false
+    }
+    __syncwarp(FULL);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (;;) {
+        // ---- census of the pool
+        int sk[K];
+        int n_t = 0, n_e = 0, n_l = 0, n_r = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            sk[k] = (int)(PW(PF_FLAGS, lane + 32 * k) & 0xffu);
+            n_t += __popc(__ballot_sync(FULL, sk[k] == ST_DESC || sk[k] == ST_RET));
+            n_e += __popc(__ballot_sync(FULL, sk[k] == ST_ENTER));
+            n_l += __popc(__ballot_sync(FULL, sk[k] == ST_LEAF));
+            n_r += __popc(__ballot_sync(FULL, sk[k] == ST_DONE));
+        }
+        if ((n_t | n_e | n_l | n_r) == 0) break;                           // every slot is ST_EXIT
+        // ---- pick the kind of step with the most waiting rays (regeneration only in batches)
+        const int c_r = (n_r >= tn.c_min || (n_t | n_e | n_l) == 0) ? n_r : 0;
+        int kind = 0, best = n_l;                                           // 0 = triangle, 1 = traversal, 2 = enter, 3 = regen
+        if (n_t > best) { kind = 1; best = n_t; }
+        if (n_e > best) { kind = 2; best = n_e; }
+        if (c_r > best) { kind = 3; best = c_r; }
+        if (best == 0) { kind = 3; }                                        // only finished rays below c_min are left: cannot happen (c_r covers it)
+        // ---- gather up to 32 rays of that kind onto the lanes
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool mine = kind == 0 ? sk[k] == ST_LEAF : (kind == 1 ? (sk[k] == ST_DESC || sk[k] == ST_RET) : (kind == 2 ? sk[k] == ST_ENTER : sk[k] == ST_DONE));
+            const unsigned b = __ballot_sync(FULL, mine);
+            const int rank = base + __popc(b & lt_mask);
+            if (mine && rank < 32) sel[rank] = (uint32_t)(lane + 32 * k);
+            base += __popc(b);
+        }
+        __syncwarp(FULL);
+        const int n_sel = base < 32 ? base : 32;
+        const bool act = lane < n_sel;
+        const int slot = act ? (int)sel[lane] : 0;
+        TravLane L;
+        L.stack = gstack + (size_t)(gslot0 + slot) * kStackWords;
+        if (kind == 0) {
+            // ---- triangle tests
+            if (act) {
+                L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
+                L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
+                L.child = PW(PF_CHILD, slot); L.i = (int)PW(PF_I, slot);
+                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
+                L.state = ST_LEAF;
+            } else L.state = ST_EXIT;
+            for (int b = 0; b < tn.burst_l; ++b) {
+                if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, &cn);
+                if (!__any_sync(FULL, L.state == ST_LEAF)) break;
+            }
+            if (act) {
+                PW(PF_I, slot) = (uint32_t)L.i;
+                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
+                if (L.state != ST_LEAF) PW(PF_FLAGS, slot) = (PW(PF_FLAGS, slot) & ~0xffu) | (uint32_t)L.state;
+            }
+        } else if (kind == 1) {
+            // ---- traversal steps: stack pops + branch visits
+            uint32_t fl = 0u;
+            if (act) {
+                L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
+                L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
+                L.dfx = u2f(PW(PF_DFX, slot)); L.dfy = u2f(PW(PF_DFY, slot)); L.dfz = u2f(PW(PF_DFZ, slot));
+                L.child = PW(PF_CHILD, slot); L.meta = PW(PF_META, slot); L.sp = (int)PW(PF_SP, slot);
+                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
+                fl = PW(PF_FLAGS, slot);
+                L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u;
+            } else L.state = ST_EXIT;
+            for (int b = 0; b < tn.burst_t; ++b) {
+                if (L.state == ST_RET) ret_step(sc, L);
+                if (L.state == ST_DESC) desc_step<COUNT>(sc, L, &cn);
+                if (!__any_sync(FULL, L.state == ST_DESC || L.state == ST_RET)) break;
+            }
+            if (act) {
+                PW(PF_CHILD, slot) = L.child; PW(PF_META, slot) = L.meta; PW(PF_SP, slot) = (uint32_t)L.sp;
+                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
+                PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)L.state;
+            }
+        } else if (kind == 2) {
+            // ---- leaf entry: record fetch + conservative culling
+            if (act) {
+                L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
+                L.dfx = u2f(PW(PF_DFX, slot)); L.dfy = u2f(PW(PF_DFY, slot)); L.dfz = u2f(PW(PF_DFZ, slot));
+                L.dfac = u2f(PW(PF_DFAC, slot));
+                L.child = PW(PF_CHILD, slot); L.meta = PW(PF_META, slot);
+                const uint32_t fl = PW(PF_FLAGS, slot);
+                L.safe = ((fl >> 8) & 1u) != 0u;
+                L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f; L.i = 0;
+                L.state = ST_ENTER;
+                enter_step<COUNT>(sc, L, &cn);
+                PW(PF_CHILD, slot) = L.child; PW(PF_I, slot) = (uint32_t)L.i; PW(PF_CTRI, slot) = (uint32_t)L.cur.tri;
+                PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)L.state;
+            }
+        } else {
+            // ---- regeneration: consume the finished hit, shade, start the next ray (or the next sample)
+            if (act) {
+                L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
+                L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
+                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
+                L.dfx = L.dfy = L.dfz = 0.0f; L.dfac = 0.0f; L.child = 0u; L.meta = 0u; L.i = 0; L.sp = 0; L.safe = true; L.sgn = 0u;
+                L.state = ST_DONE;
+                PathRay q;
+                uint4 *gp = gpath + 2 * (gslot0 + slot);
+                const uint4 g0 = gp[0], g1 = gp[1];
+                const uint32_t pf = g1.y;
+                q.sidx = g0.x; q.j = (int)g0.y;
+                q.stream = (unsigned long long)g0.z | ((unsigned long long)g0.w << 32);
+                q.saved_r = u2f(g1.x); q.saved_j = (int)(pf & 0xffffu) - 1;
+                q.any_emit = ((pf >> 16) & 1u) != 0u; q.in_flight = ((pf >> 17) & 1u) != 0u;
+                path_regen<COUNT>(sc, p, rd, fetch, st, q, gpm + (size_t)(gslot0 + slot) * SQT_MAX_DEPTH, L, &cn);
+                PW(PF_OX, slot) = f2u(L.r.ox); PW(PF_OY, slot) = f2u(L.r.oy); PW(PF_OZ, slot) = f2u(L.r.oz);
+                PW(PF_DX, slot) = f2u(L.r.dx); PW(PF_DY, slot) = f2u(L.r.dy); PW(PF_DZ, slot) = f2u(L.r.dz);
+                PW(PF_DFX, slot) = f2u(L.dfx); PW(PF_DFY, slot) = f2u(L.dfy); PW(PF_DFZ, slot) = f2u(L.dfz);
+                PW(PF_CHILD, slot) = L.child; PW(PF_META, slot) = L.meta; PW(PF_I, slot) = (uint32_t)L.i;
+                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
+                PW(PF_SP, slot) = (uint32_t)L.sp; PW(PF_DFAC, slot) = f2u(L.dfac);
+                PW(PF_FLAGS, slot) = (uint32_t)L.state | (L.safe ? 0x100u : 0u) | (L.sgn << 16);
+                gp[0] = make_uint4(q.sidx, (uint32_t)q.j, (uint32_t)q.stream, (uint32_t)(q.stream >> 32));
+                gp[1] = make_uint4(f2u(q.saved_r), (uint32_t)(q.saved_j + 1) | (q.any_emit ? 0x10000u : 0u) | (q.in_flight ? 0x20000u : 0u), 0u, 0u);
+            }
+        }
+        __syncwarp(FULL);
+    }
+#undef PW
+    flush_stats(ds, st, cn, COUNT);
+}
+
 // sum the round's samples into the per-pixel running sums, in sample order (Lib.hs:88)
 __global__ void __launch_bounds__(256) k_accumulate(RenderParams p, RoundInfo rd, float *__restrict__ accum, const DeviceStats *ds) {
     if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
@@ -309,6 +473,10 @@ struct sqt_ctx {
     // pinned host staging for image I/O
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
     Tune tune = {8, 1, 8};
+    int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
+    PoolTune pool_tune = {4, 8, 16};
+    int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1
+    uint32_t *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0;
     // group
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -351,6 +519,12 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
     for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
     CU(cudaMalloc(&c->d_stats, sizeof(DeviceStats)));
     CU(cudaMallocHost(&c->h_stats, sizeof(DeviceStats)));
+    if (const char *t = getenv("SQT_POOL")) { int k = atoi(t); if (k >= 0 && k <= 4) c->pool_k = k; }
+    if (const char *t = getenv("SQT_POOL_BLOCKS")) c->pool_blocks = atoi(t);
+    if (const char *t = getenv("SQT_POOL_TUNE")) {
+        int a, b, cm;
+        if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->pool_tune = {a, b, cm};
+    }
     if (const char *t = getenv("SQT_SBUF_MB")) { long long mb = atoll(t); if (mb > 0) c->sbuf_budget = mb << 20; }
     if (const char *t = getenv("SQT_TUNE")) {        // "a_leave,b_leave,c_min" -- scheduling knobs only, results do not depend on them
         int a, b, cm;
@@ -370,7 +544,7 @@ extern "C" int sqt_destroy(sqt_ctx *c) {
     cudaSetDevice(c->device);
     if (c->comm && nccl_api()->lib) nccl_api()->CommDestroy(c->comm);
     free_scene(c);
-    cudaFree(c->d_prim); cudaFree(c->d_accum); cudaFree(c->d_rgb8); cudaFree(c->d_stats); cudaFree(c->d_pixel_list); cudaFree(c->d_sbuf);
+    cudaFree(c->d_prim); cudaFree(c->d_accum); cudaFree(c->d_rgb8); cudaFree(c->d_stats); cudaFree(c->d_pixel_list); cudaFree(c->d_sbuf); cudaFree(c->d_gstack); cudaFree(c->d_gpm); cudaFree(c->d_gpath);
     cudaFree(c->d_org); cudaFree(c->d_dir); cudaFree(c->d_dist); cudaFree(c->d_point); cudaFree(c->d_tri);
     cudaFreeHost(c->h_stats); cudaFreeHost(c->h_rgb8); cudaFreeHost(c->h_accum);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -475,6 +649,45 @@ static int persistent_grid(sqt_ctx *ctx, K kernel, long long nwork) {
     long long grid = (long long)ctx->sm_count * per_sm, want = (nwork + 127) / 128;
     if (want < grid) grid = want ? want : 1;
     return (int)grid;
+}
+template <bool COUNT, int K>
+static int launch_pool(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems) {
+    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 32) * sizeof(uint32_t);
+    auto kern = k_paths_pool<COUNT, K>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (ctx->pool_blocks > 0 && ctx->pool_blocks < per_sm) {
+        // keep the rest of the 228 KB for L1: the triangle / node / stack working set lives there
+        per_sm = ctx->pool_blocks;
+        int pct = (int)((smem + 1024) * per_sm * 100 / (228 * 1024)) + 1;
+        if (pct > 100) pct = 100;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+    long long grid = (long long)ctx->sm_count * per_sm, want = (nitems + 128 * K - 1) / (128 * K);
+    if (want < grid) grid = want ? want : 1;
+    const long long slots = grid * 4 * 32 * K;
+    if (slots > ctx->cap_pool_slots) {
+        cudaFree(ctx->d_gstack); cudaFree(ctx->d_gpm); cudaFree(ctx->d_gpath);
+        ctx->d_gstack = nullptr; ctx->d_gpm = nullptr; ctx->d_gpath = nullptr; ctx->cap_pool_slots = 0;
+        const long long cap = (long long)ctx->sm_count * 16 * 4 * 32 * K > slots ? (long long)ctx->sm_count * 16 * 4 * 32 * K : slots;
+        CU(cudaMalloc(&ctx->d_gstack, (size_t)cap * kStackWords * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->d_gpm, (size_t)cap * SQT_MAX_DEPTH * sizeof(uint16_t)));
+        CU(cudaMalloc(&ctx->d_gpath, (size_t)cap * 2 * sizeof(uint4)));
+        ctx->cap_pool_slots = cap;
+    }
+    kern<<<(int)grid, 128, smem, ctx->stream>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->pool_tune, ctx->d_gstack, ctx->d_gpm, ctx->d_gpath);
+    CU(cudaGetLastError());
+    return SQT_OK;
+}
+template <bool COUNT>
+static int launch_pool_k(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems) {
+    switch (ctx->pool_k) {
+    case 1: return launch_pool<COUNT, 1>(ctx, d, rd, round, nitems);
+    case 2: return launch_pool<COUNT, 2>(ctx, d, rd, round, nitems);
+    case 3: return launch_pool<COUNT, 3>(ctx, d, rd, round, nitems);
+    default: return launch_pool<COUNT, 4>(ctx, d, rd, round, nitems);
+    }
 }
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
@@ -589,7 +802,10 @@ static int enqueue_render(sqt_ctx *ctx, const RenderParams &d, bool count, uint3
         for (int kb = k0; kb < k1; kb += S, ++round) {
             rd.k0 = kb; rd.k1 = kb + S < k1 ? kb + S : k1;
             CU(cudaMemsetAsync(ctx->d_sbuf, 0, (size_t)(nwork * (long long)(rd.k1 - rd.k0) * 12ll), st));
-            if (count) k_paths<true><<<persistent_grid(ctx, k_paths<true>, nwork << rd.log2_s), 128, 0, st>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->tune);
+            if (ctx->pool_k > 0) {
+                rc = count ? launch_pool_k<true>(ctx, d, rd, round, nwork << rd.log2_s) : launch_pool_k<false>(ctx, d, rd, round, nwork << rd.log2_s);
+                if (rc) return rc;
+            } else if (count) k_paths<true><<<persistent_grid(ctx, k_paths<true>, nwork << rd.log2_s), 128, 0, st>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->tune);
             else k_paths<false><<<persistent_grid(ctx, k_paths<false>, nwork << rd.log2_s), 128, 0, st>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->tune);
             CU(cudaGetLastError()); nl++;
             k_accumulate<<<agrid > 0 ? agrid : 1, 256, 0, st>>>(d, rd, ctx->d_accum, ctx->d_stats);

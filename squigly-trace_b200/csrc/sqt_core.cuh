@@ -338,18 +338,29 @@ SQT_HD void desc_step(const SceneView &sc, TravLane &L, Counters *cn) {
 // One triangle of the leaf (BIH.hs:105-109): V.mapMaybe over the leaf's triangles, minimumBy (comparing dist).
 // base-4.9 minimumBy = foldr1 min' with min' x y = GT -> y ; _ -> x : walk from the last triangle
 // to the first, the earlier one wins unless it is strictly farther.
-template <bool COUNT>
-SQT_HD void tri_step(const SceneView &sc, TravLane &L, Counters *cn) {
-    const uint32_t idx = L.child + (uint32_t)L.i;
+// the three 128-bit words of triangle `idx` (leaf order)
+struct TriData { float4 a0, a1, a2; };
+SQT_HD TriData tri_load(const SceneView &sc, uint32_t idx) {
     const float4 *p = sc.tris + 3 * (size_t)idx;
-    const float4 a0 = SQT_LDG4(p), a1 = SQT_LDG4(p + 1), a2 = SQT_LDG4(p + 2);
+    TriData d; d.a0 = SQT_LDG4(p); d.a1 = SQT_LDG4(p + 1); d.a2 = SQT_LDG4(p + 2);
+    return d;
+}
+// test the already loaded triangle L.child + L.i and advance (split from the load so that callers can prefetch)
+template <bool COUNT>
+SQT_HD void tri_apply(TravLane &L, const TriData &d, Counters *cn) {
+    const uint32_t idx = L.child + (uint32_t)L.i;
     float t, dist;
     int stage;
-    if (moller_trumbore(a0, a1, a2, L.r, t, dist, stage)) {
+    if (moller_trumbore(d.a0, d.a1, d.a2, L.r, t, dist, stage)) {
         if (L.cur.tri < 0 || !cmp_gt(dist, L.cur.dist)) { L.cur.tri = (int)idx; L.cur.t = t; L.cur.dist = dist; }
     }
     if (COUNT) { cn->mt_pass_a += stage >= 1; cn->mt_pass_u += stage >= 2; cn->mt_pass_v += stage >= 3; cn->mt_accept += stage >= 4; }
     if (--L.i < 0) L.state = ST_RET;
+}
+template <bool COUNT>
+SQT_HD void tri_step(const SceneView &sc, TravLane &L, Counters *cn) {
+    const TriData d = tri_load(sc, L.child + (uint32_t)L.i);
+    tri_apply<COUNT>(L, d, cn);
 }
 
 // A subtree returned `cur`: pop entries until one of them sends the lane into a far subtree (-> ST_DESC) or

@@ -78,102 +78,110 @@ struct RoundInfo {
     int k0, k1;                // samples [k0, k1) of this round, k1 - k0 <= S
 };
 
+// per-ray integrator state (what a lane -- or a pool slot -- has to remember between two rays of one path)
+struct PathRay {
+    uint32_t sidx;                           // index of the current sample in sbuf (without the *3)
+    int j;                                   // bounce index of the hit being shaded
+    unsigned long long stream;               // generator seed of the current sample: spp*(x + y*w) + k
+    float saved_r; int saved_j;              // draw j+1 of a scatter is draw j of the next bounce
+    bool any_emit, in_flight;
+};
+SQT_HD void path_ray_init(PathRay &q) { q.sidx = 0u; q.j = 0; q.stream = 0ull; q.saved_r = 0.0f; q.saved_j = -1; q.any_emit = false; q.in_flight = false; }
+
+SQT_HD float path_draw(const RenderParams &p, PathRay &q, uint32_t jj) {
+    if ((int)jj == q.saved_j) return q.saved_r;
+    uint32_t w[4];
+    philox4x32_10((uint32_t)q.stream, (uint32_t)(q.stream >> 32), jj >> 2, 0x52545153u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), w);
+    const uint32_t k = jj & 3u;
+    return random_r01(k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3])));
+}
+
+// called when L.state == ST_DONE: consume the hit (if a ray was in flight), then shade / start the next sample until
+// the slot has a ray to trace (-> start_ray) or the queue is empty (-> ST_EXIT).  pm: SQT_MAX_DEPTH entries of
+// ray-private memory holding the material of every shaded bounce of the current path.
+template <bool COUNT, class Fetch>
+SQT_HD void path_regen(const SceneView &sc, const RenderParams &p, const RoundInfo &rd, Fetch &fetch, PathStats &st, PathRay &q,
+                       uint16_t *pm, TravLane &L, Counters *cn) {
+    bool path_over = false;
+    int htri = -1; float ht = 0.0f;
+    if (q.in_flight) {                                    // the ray of Lib.hs:131 came back
+        q.in_flight = false;
+        st.rays += 1;
+        if (L.cur.tri >= 0) { htri = L.cur.tri; ht = L.cur.t; q.j += 1; }
+        else path_over = true;
+    }
+    for (;;) {
+        if (path_over) {
+            // ---- the sample is finished: store its radiance (samples that never met an emitter are exactly +0,
+            //      which the zero-filled buffer already holds)
+            if (q.any_emit) {
+                float lr, lg, lb;
+                fold_path(sc, pm, q.j, lr, lg, lb);
+                rd.sbuf[3 * (size_t)q.sidx] = lr; rd.sbuf[3 * (size_t)q.sidx + 1] = lg; rd.sbuf[3 * (size_t)q.sidx + 2] = lb;
+            }
+            st.samples += 1;
+            path_over = false;
+            htri = -1;
+        }
+        if (htri < 0) {
+            // ---- next sample
+            const long long w = fetch();
+            if (w < 0) { L.state = ST_EXIT; return; }
+            const long long slot = w >> rd.log2_s;
+            const int ks = (int)(w & ((1ll << rd.log2_s) - 1));
+            const int k = rd.k0 + ks;
+            if (k >= rd.k1) continue;
+            const long long pixel = rd.pixel_list ? (long long)rd.pixel_list[slot] : work_to_pixel(p, slot);
+            if (pixel < 0) continue;
+            const int py = (int)(pixel / p.cols), px = (int)(pixel % p.cols);
+            q.stream = (unsigned long long)p.spp * ((unsigned long long)px + (unsigned long long)py * (unsigned long long)p.seed_stride)
+                       + (unsigned long long)k;
+            q.sidx = (uint32_t)((long long)ks * rd.slot_stride + slot);
+            q.any_emit = false; q.saved_j = -1;
+            L.r = make_ray(p, py, px);
+            if (rd.prim) {
+                // the primary ray is the same for every sample of a pixel (Lib.hs:81): its hit was traced once
+                const int2 ph = rd.prim[pixel];
+                htri = ph.x; ht = u2f((uint32_t)ph.y); q.j = 0;
+                st.primary_reused += 1;
+            } else {                                      // primary reuse off: trace it again like Lib.hs:84 does
+                q.j = -1; q.in_flight = true; start_ray<COUNT>(sc, L, cn); return;
+            }
+        }
+        // ---- shade the hit of bounce j (raytrace, Lib.hs:127-137); L.r is the ray that produced it
+        const float4 *tp = sc.tris + 3 * (size_t)htri;
+        const uint32_t mat = f2u(SQT_LDG4(tp + 2).y);
+        pm[q.j] = (uint16_t)mat;
+        const float4 *mp = sc.mats + 3 * (size_t)mat;
+        const float4 m0 = SQT_LDG4(mp);
+        const uint32_t mflags = f2u(SQT_LDG4(mp + 2).w);
+        q.any_emit = q.any_emit || (mflags & kMatEmits);
+        const bool terminal = (q.j + 1 > p.max_depth - 1) || (p.terminate_on_black && (mflags & kMatBlack));
+        if (terminal) { path_over = true; continue; }
+        // bounceRay (Lib.hs:155-160)
+        const float x = path_draw(p, q, (uint32_t)q.j);
+        float v = 0.0f;
+        const bool scatter = m0.x < x;
+        if (scatter) { v = path_draw(p, q, (uint32_t)q.j + 1u); q.saved_r = v; q.saved_j = q.j + 1; } else q.saved_j = -1;
+        L.r = bounce_ray(sc, L.r, htri, ht, scatter, x, v);
+        q.in_flight = true;
+        start_ray<COUNT>(sc, L, cn);
+        return;
+    }
+}
+
 template <class Fetch>
 struct PathPolicy {
     const RenderParams &p;
     const RoundInfo &rd;
     Fetch &fetch;
     PathStats &st;
-    // per-lane path state
-    long long sidx = 0;                      // index of the current sample in sbuf (without the *3)
-    int j = 0;                               // bounce index of the hit being shaded
-    unsigned long long stream = 0ull;        // generator seed of the current sample: spp*(x + y*w) + k
-    float saved_r = 0.0f; int saved_j = -1;  // draw j+1 of a scatter is draw j of the next bounce
-    bool any_emit = false, in_flight = false;
-    uint16_t *pm;                            // SQT_MAX_DEPTH entries of lane-private memory: material of every
-                                             // shaded bounce of the current path
-
+    PathRay q;
+    uint16_t *pm;
     SQT_HD PathPolicy(const RenderParams &p_, const RoundInfo &rd_, Fetch &f_, PathStats &st_, uint16_t *pm_)
-        : p(p_), rd(rd_), fetch(f_), st(st_), pm(pm_) {}
-
-    SQT_HD float draw_r(uint32_t jj) {
-        if ((int)jj == saved_j) return saved_r;
-        uint32_t w[4];
-        philox4x32_10((uint32_t)stream, (uint32_t)(stream >> 32), jj >> 2, 0x52545153u, (uint32_t)p.seed,
-                      (uint32_t)(p.seed >> 32), w);
-        const uint32_t q = jj & 3u;
-        return random_r01(q == 0 ? w[0] : (q == 1 ? w[1] : (q == 2 ? w[2] : w[3])));
-    }
-
+        : p(p_), rd(rd_), fetch(f_), st(st_), pm(pm_) { path_ray_init(q); }
     template <bool COUNT>
-    SQT_HD void regen(const SceneView &sc, TravLane &L, Counters *cn) {
-        bool path_over = false;
-        int htri = -1; float ht = 0.0f;
-        if (in_flight) {                                  // the ray of Lib.hs:131 came back
-            in_flight = false;
-            st.rays += 1;
-            if (L.cur.tri >= 0) { htri = L.cur.tri; ht = L.cur.t; j += 1; }
-            else path_over = true;
-        }
-        for (;;) {
-            if (path_over) {
-                // ---- the sample is finished: store its radiance (samples that never met an emitter are exactly +0,
-                //      which the zero-filled buffer already holds)
-                if (any_emit) {
-                    float lr, lg, lb;
-                    fold_path(sc, pm, j, lr, lg, lb);
-                    rd.sbuf[3 * sidx] = lr; rd.sbuf[3 * sidx + 1] = lg; rd.sbuf[3 * sidx + 2] = lb;
-                }
-                st.samples += 1;
-                path_over = false;
-                htri = -1;
-            }
-            if (htri < 0) {
-                // ---- next sample
-                const long long w = fetch();
-                if (w < 0) { L.state = ST_EXIT; return; }
-                const long long slot = w >> rd.log2_s;
-                const int ks = (int)(w & ((1ll << rd.log2_s) - 1));
-                const int k = rd.k0 + ks;
-                if (k >= rd.k1) continue;
-                const long long pixel = rd.pixel_list ? (long long)rd.pixel_list[slot] : work_to_pixel(p, slot);
-                if (pixel < 0) continue;
-                const int py = (int)(pixel / p.cols), px = (int)(pixel % p.cols);
-                stream = (unsigned long long)p.spp * ((unsigned long long)px + (unsigned long long)py * (unsigned long long)p.seed_stride)
-                         + (unsigned long long)k;
-                sidx = (long long)ks * rd.slot_stride + slot;
-                any_emit = false; saved_j = -1;
-                L.r = make_ray(p, py, px);
-                if (rd.prim) {
-                    // the primary ray is the same for every sample of a pixel (Lib.hs:81): its hit was traced once
-                    const int2 ph = rd.prim[pixel];
-                    htri = ph.x; ht = u2f((uint32_t)ph.y); j = 0;
-                    st.primary_reused += 1;
-                } else {                                  // primary reuse off: trace it again like Lib.hs:84 does
-                    j = -1; in_flight = true; start_ray<COUNT>(sc, L, cn); return;
-                }
-            }
-            // ---- shade the hit of bounce j (raytrace, Lib.hs:127-137); L.r is the ray that produced it
-            const float4 *tp = sc.tris + 3 * (size_t)htri;
-            const uint32_t mat = f2u(SQT_LDG4(tp + 2).y);
-            pm[j] = (uint16_t)mat;
-            const float4 *mp = sc.mats + 3 * (size_t)mat;
-            const float4 m0 = SQT_LDG4(mp);
-            const uint32_t mflags = f2u(SQT_LDG4(mp + 2).w);
-            any_emit = any_emit || (mflags & kMatEmits);
-            const bool terminal = (j + 1 > p.max_depth - 1) || (p.terminate_on_black && (mflags & kMatBlack));
-            if (terminal) { path_over = true; continue; }
-            // bounceRay (Lib.hs:155-160)
-            const float x = draw_r((uint32_t)j);
-            float v = 0.0f;
-            const bool scatter = m0.x < x;
-            if (scatter) { v = draw_r((uint32_t)j + 1u); saved_r = v; saved_j = j + 1; } else saved_j = -1;
-            L.r = bounce_ray(sc, L.r, htri, ht, scatter, x, v);
-            in_flight = true;
-            start_ray<COUNT>(sc, L, cn);
-            return;
-        }
-    }
+    SQT_HD void regen(const SceneView &sc, TravLane &L, Counters *cn) { path_regen<COUNT>(sc, p, rd, fetch, st, q, pm, L, cn); }
 };
 
 // avg-in-order part of renderPixel (Lib.hs:87-88): add the round's samples of one slot to the pixel's running sum,

@@ -55,22 +55,27 @@ def cornell_box(target_tris=10000, seed=0x5171):
     return np.concatenate(parts), np.concatenate(mats_idx), mats
 
 
-def subdivided_mesh(target_tris=1_000_000, seed=0x5172):
-    """Config 4: a jittered height-field mesh (deep BIH, traversal bound) standing like a back wall: x, z in [-2,2],
-    y = -1 + relief, facing the camera of data/camera (at y = 7 looking down -y); one emissive quad above, diffuse."""
+def subdivided_mesh(target_tris=1_000_000, seed=0x5172, half=None):
+    """Config 4: a jittered height-field mesh (deep BIH, traversal bound) standing like a back wall behind the
+    origin, facing the camera of data/camera (at y = 7 looking down -y); one emissive quad above it, diffuse.
+    The extent grows with the triangle count so that every triangle keeps |e1 x e2| well above the reference's
+    ABSOLUTE epsilon 1e-4 (Geometry.hs:142) -- smaller triangles are simply invisible to mollerTrumbore."""
     rng = np.random.default_rng(seed)
     n = max(2, int(round(np.sqrt(target_tris / 2.0))))
-    xs = np.linspace(-2, 2, n + 1); zs = np.linspace(-2, 2, n + 1)
+    if half is None:
+        half = max(2.0, 0.03 * n)                      # edge = 2*half/n >= 0.06
+    xs = np.linspace(-half, half, n + 1); zs = np.linspace(-half, half, n + 1)
     X, Z = np.meshgrid(xs, zs, indexing="ij")
-    edge = 4.0 / n
-    Y = (-1.0 + 0.35 * np.sin(2.3 * X) * np.cos(1.7 * Z) + 0.15 * np.sin(9.1 * X + 1.0) * np.sin(7.7 * Z)
+    edge = 2.0 * half / n
+    Y = (-0.5 * half - 1.0 + 0.35 * np.sin(2.3 * X) * np.cos(1.7 * Z) + 0.15 * np.sin(9.1 * X + 1.0) * np.sin(7.7 * Z)
          + rng.uniform(-1e-3, 1e-3, X.shape) * edge)
     X = X + rng.uniform(-1e-3, 1e-3, X.shape) * edge
     Z = Z + rng.uniform(-1e-3, 1e-3, X.shape) * edge
     P = np.stack([X, Y, Z], -1)
     a, b, c, d = P[:-1, :-1], P[1:, :-1], P[1:, 1:], P[:-1, 1:]
     tris = np.concatenate([np.concatenate([a, b, c], -1).reshape(-1, 9), np.concatenate([a, c, d], -1).reshape(-1, 9)])
-    light = _quad_grid([-0.7, 0.2, 1.95], [1.4, 0, 0], [0, 1.4, 0], 1, 1)
+    q = 0.35 * half
+    light = _quad_grid([-q, -0.5 * half + 1.5, 0.45 * half], [2 * q, 0, 0], [0, 2 * q, 0], 1, 1)
     v9 = np.concatenate([tris.astype(np.float32), light])
     mi = np.concatenate([np.zeros(len(tris), np.int32), np.ones(len(light), np.int32)])
     mats = np.array([[0.0, 0.7, 0.7, 0.7, 0, 0, 0, 0], [0.0, 0, 0, 0, 100, 1, 1, 1]], np.float32)
@@ -78,8 +83,10 @@ def subdivided_mesh(target_tris=1_000_000, seed=0x5172):
 
 
 def triangle_soup(n_tris=10_000_000, seed=0x5173, all_reflective=True):
-    """Config 5: centroids ~U([-1,1]^3), edge length ~U(0.002,0.02), random orientation, materials reflective=1,
-    one in 64 triangles emissive."""
+    """Config 5 as BASELINE.json specifies it: centroids ~U([-1,1]^3), edge length ~U(0.002,0.02), random
+    orientation, materials reflective=1, one in 64 triangles emissive.  Note: |e1 x e2| of most of these triangles is
+    below the reference's absolute epsilon 1e-4 (Geometry.hs:142), so mollerTrumbore rejects them at the `a` guard --
+    that is the reference's behaviour and both the oracle and the device reproduce it."""
     rng = np.random.default_rng(seed)
     c = rng.uniform(-1, 1, (n_tris, 3))
     L = rng.uniform(0.002, 0.02, (n_tris, 1))
