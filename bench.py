@@ -34,7 +34,7 @@ for p in (ROOT, PKG):
 WIDTH, HEIGHT, SPP, DEPTH, SEED = 1920, 1080, 1024, 8, 0
 DATA = os.path.join(ROOT, "data")
 WORKLOAD = "data/scene.obj 1920x1080 1024spp depth8"
-NCU_DRAM_BYTES_PER_LAUNCH = 193057536 + 169222400      # profiles/r01_k_paths_v3_rounds.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 2267319000 + 22123130000     # profiles/r01_k_paths_v4_pool.txt
 
 
 class ClockSampler:
@@ -256,10 +256,11 @@ def run_ours(args, rank, world, local_rank):
         achieved = ops / (k_ms * 1e-3) / 1e12
         mem_bytes = 16 * ref_cnt["branch_visits"] + 36 * ref_cnt["tri_tests"]
         keys = ("rays_traced", "branch_visits", "child_box_tests", "tri_tests", "mt_pass_a", "mt_pass_u", "mt_pass_v", "mt_accept", "leaves_culled")
-        roof = {"bound": "fp32", "kernel": "k_paths", "achieved": achieved, "peak": fp32_peak / 1e3, "unit": "TFLOP/s",
+        roof = {"bound": "fp32", "kernel": "k_paths_pool", "achieved": achieved, "peak": fp32_peak / 1e3, "unit": "TFLOP/s",
                 "frac": achieved / (fp32_peak / 1e3), "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 64-spp k_paths launch (the bench issues 16 such "
-                                  "launches per frame), ncu --set full, profiles/r01_k_paths_v3_rounds.txt",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 64-spp k_paths_pool launch (the bench issues 16 such "
+                                  "launches per frame), ncu --set full, profiles/r01_k_paths_v4_pool.txt; almost all of it is write-back of "
+                                  "the per-slot traversal stacks, which live in global memory in the pool kernel",
                 "peak_source": "measured live: non-fused FADD/FMUL issue rate of this GPU (sqt_measure_fp32_peak); FMA contraction is "
                                "forbidden on the bit-exact path, so this is the FP32 ceiling (MEASURED_PEAKS.json has no FP32 figure)",
                 "kernel_ms": k_ms, "kernel_ms_note": "all k_paths + k_accumulate launches of one frame (one pair per 64-spp round)",
