@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, Rou
 // up to 32 of them onto its lanes (rank by ballot, scatter slot ids through shared memory), runs a short burst of
 // that one kind of step with (nearly) all lanes active, and writes the rays back.  With one ray per lane at most
 // ~10 of 32 lanes share a step kind at any time (tools/sched_sim.py); regrouping rays lifts that limit.
+#ifndef SQT_POOL_MIN_BLOCKS
+#define SQT_POOL_MIN_BLOCKS 8
+#endif
 struct PoolTune { int burst_t, burst_l, c_min; };
 
 enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_META, PF_I, PF_CTRI, PF_CT, PF_CDIST,
@@ -200,7 +203,7 @@ enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_
 // the integrator state of a slot (PathRay) is only touched by regeneration: 8 words per slot in global memory
 
 template <bool COUNT, int K>
-__global__ void __launch_bounds__(128) k_paths_pool(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, PoolTune tn,
+__global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, PoolTune tn,
                                                     uint32_t *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath) {
     extern __shared__ uint32_t pool_smem[];
     constexpr int P = 32 * K;
