@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, Rou
 #ifndef SQT_POOL_MIN_BLOCKS
 #define SQT_POOL_MIN_BLOCKS 8
 #endif
-struct PoolTune { int burst_t, burst_l, c_min; };
+struct PoolTune { int burst_t, burst_l, c_min, merge_enter; };   // merge_enter: leaf entry runs inside the traversal burst
 
 enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_META, PF_I, PF_CTRI, PF_CT, PF_CDIST,
        PF_SP, PF_FLAGS, PF_DFAC, PF_WORDS };      // 18 words = 72 B per ray in shared memory
@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             sk[k] = (int)(PW(PF_FLAGS, lane + 32 * k) & 0xffu);
-            n_t += __popc(__ballot_sync(FULL, sk[k] == ST_DESC || sk[k] == ST_RET));
-            n_e += __popc(__ballot_sync(FULL, sk[k] == ST_ENTER));
+            n_t += __popc(__ballot_sync(FULL, sk[k] == ST_DESC || sk[k] == ST_RET || (tn.merge_enter && sk[k] == ST_ENTER)));
+            n_e += __popc(__ballot_sync(FULL, !tn.merge_enter && sk[k] == ST_ENTER));
             n_l += __popc(__ballot_sync(FULL, sk[k] == ST_LEAF));
             n_r += __popc(__ballot_sync(FULL, sk[k] == ST_DONE));
         }
@@ -251,7 +251,9 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         int base = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const bool mine = kind == 0 ? sk[k] == ST_LEAF : (kind == 1 ? (sk[k] == ST_DESC || sk[k] == ST_RET) : (kind == 2 ? sk[k] == ST_ENTER : sk[k] == ST_DONE));
+            const bool mine = kind == 0 ? sk[k] == ST_LEAF
+                            : (kind == 1 ? (sk[k] == ST_DESC || sk[k] == ST_RET || (tn.merge_enter && sk[k] == ST_ENTER))
+                                         : (kind == 2 ? sk[k] == ST_ENTER : sk[k] == ST_DONE));
             const unsigned b = __ballot_sync(FULL, mine);
             const int rank = base + __popc(b & lt_mask);
             if (mine && rank < 32) sel[rank] = (uint32_t)(lane + 32 * k);
@@ -290,15 +292,18 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 L.dfx = u2f(PW(PF_DFX, slot)); L.dfy = u2f(PW(PF_DFY, slot)); L.dfz = u2f(PW(PF_DFZ, slot));
                 L.child = PW(PF_CHILD, slot); L.meta = PW(PF_META, slot); L.sp = (int)PW(PF_SP, slot);
                 L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
+                L.dfac = u2f(PW(PF_DFAC, slot)); L.i = (int)PW(PF_I, slot);
                 fl = PW(PF_FLAGS, slot);
                 L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u;
             } else L.state = ST_EXIT;
             for (int b = 0; b < tn.burst_t; ++b) {
                 if (L.state == ST_RET) ret_step(sc, L);
                 if (L.state == ST_DESC) desc_step<COUNT>(sc, L, &cn);
+                if (tn.merge_enter && L.state == ST_ENTER) enter_step<COUNT>(sc, L, &cn);     // culled lanes fall back to ST_RET
                 if (!__any_sync(FULL, L.state == ST_DESC || L.state == ST_RET)) break;
             }
             if (act) {
+                PW(PF_I, slot) = (uint32_t)L.i;
                 PW(PF_CHILD, slot) = L.child; PW(PF_META, slot) = L.meta; PW(PF_SP, slot) = (uint32_t)L.sp;
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
                 PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)L.state;
@@ -477,7 +482,7 @@ struct sqt_ctx {
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
     Tune tune = {8, 1, 8};
     int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
-    PoolTune pool_tune = {4, 8, 16};
+    PoolTune pool_tune = {4, 8, 16, 0};
     int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1
     uint32_t *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0;
     // group
@@ -525,8 +530,8 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
     if (const char *t = getenv("SQT_POOL")) { int k = atoi(t); if (k >= 0 && k <= 4) c->pool_k = k; }
     if (const char *t = getenv("SQT_POOL_BLOCKS")) c->pool_blocks = atoi(t);
     if (const char *t = getenv("SQT_POOL_TUNE")) {
-        int a, b, cm;
-        if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->pool_tune = {a, b, cm};
+        int a, b, cm, me = 0;
+        if (sscanf(t, "%d,%d,%d,%d", &a, &b, &cm, &me) >= 3) c->pool_tune = {a, b, cm, me};
     }
     if (const char *t = getenv("SQT_SBUF_MB")) { long long mb = atoll(t); if (mb > 0) c->sbuf_budget = mb << 20; }
     if (const char *t = getenv("SQT_TUNE")) {        // "a_leave,b_leave,c_min" -- scheduling knobs only, results do not depend on them
