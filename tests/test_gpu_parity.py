@@ -271,6 +271,30 @@ def test_every_path_kernel_scheduler_is_bit_exact(host_scene, oracle_scene, came
     ctx.close()
 
 
+def test_schedulers_and_culling_agree_at_full_size(host_scene, camera, monkeypatch):
+    """The bench frame (1920x1080, depth 8) at 32 spp -- 170 M rays -- rendered four ways: ray pools (default), one ray per
+    lane, ray pools without the leaf culling, and ray pools without primary reuse / early termination.  All four
+    accumulation buffers must be bit-identical, and the last one must trace strictly more rays."""
+    p = pysqt.make_params(1920, 1080, 32, max_depth=8, seed=21)
+    results = {}
+    for name, pool, cull, flags in [("pool", "2", True, 0), ("lane", "0", True, 0), ("pool-nocull", "2", False, 0),
+                                    ("pool-reference-work", "2", True, pysqt.SQT_F_NO_PRIMARY_REUSE | pysqt.SQT_F_NO_EARLY_TERMINATION)]:
+        monkeypatch.setenv("SQT_POOL", pool)
+        ctx = pysqt.Context(0)
+        ctx.upload(host_scene)
+        ctx.set_leaf_cull(cull)
+        pp = pysqt.make_params(1920, 1080, 32, max_depth=8, seed=21, flags=flags)
+        out = ctx.render(camera, pp, want_rgb8=False)
+        results[name] = (out["accum"], out["stats"])
+        ctx.close()
+    base = results["pool"][0]
+    for name, (acc, st) in results.items():
+        assert np.array_equal(bits(acc), bits(base)), name
+        assert st["samples"] == 1920 * 1080 * 32
+    assert results["pool"][1]["rays_traced"] == results["lane"][1]["rays_traced"] == results["pool-nocull"][1]["rays_traced"]
+    assert results["pool-reference-work"][1]["rays_traced"] > results["pool"][1]["rays_traced"]
+
+
 def test_render_is_deterministic_and_seed_sensitive(gpu_ctx, host_scene, camera):
     gpu_ctx.upload(host_scene)
     p = pysqt.make_params(64, 64, 16, max_depth=4, seed=11)
