@@ -69,6 +69,17 @@ typedef struct sqt_material {
     float reflective, surf_color[3], emissive, emit_color[3];
 } sqt_material;                          /* 32 B */
 
+/* EXTENSION (named by the north star; the reference has no sphere primitive or syntax, so the semantics are this
+ * library's own and are restated in oracle/oracle.c): analytic, double-sided spheres tested after the BIH for
+ * every ray; the closest of the BIH hit and the sphere hits wins, earlier candidates win ties.  In tri_out a
+ * sphere k is reported as n_tris + k. */
+typedef struct sqt_sphere {
+    float center[3];
+    float radius;
+    uint32_t material;                   /* index into mats[] */
+    uint32_t pad[3];
+} sqt_sphere;                            /* 32 B */
+
 typedef struct sqt_scene_desc {
     float root_bounds[6];                /* bounds of BIH (BIH.hs:41,62-65): lo.xyz, hi.xyz */
     const sqt_node *nodes;  uint32_t n_nodes;
@@ -132,6 +143,9 @@ const char *sqt_last_error(const sqt_ctx *ctx);        /* ctx may be NULL: error
 
 /* replaces the in-memory `Scene BIH` value handed to render (Main.hs:39,55-56) ------------- */
 int sqt_upload_scene(sqt_ctx *ctx, const sqt_scene_desc *scene);
+
+/* optional, after sqt_upload_scene: n = 0 removes the spheres again */
+int sqt_upload_spheres(sqt_ctx *ctx, const sqt_sphere *spheres, uint32_t n);
 
 /* batched Scene.intersect (Geometry.hs:64; intersectBIH BIH.hs:101-141) ---------------------
  * org/dir: n x 3 floats, xyz interleaved.  tri_out[i] = orig_index of the closest hit or -1.

@@ -82,9 +82,12 @@ typedef struct {
     int first, count;    /* Leaf: range in leaf_tris[] */
 } bnode;
 
+typedef struct { v3 c; float r; int mat; } sphere;     /* EXTENSION: no counterpart in the reference (see include/sqt.h) */
+
 typedef struct {
     triangle *tris; int n_tris;
     material *mats; int n_mats;
+    sphere *spheres; int n_spheres;
     /* BIH */
     bounds root; bnode *nodes; int n_nodes, cap_nodes;
     int *leaf_tris; int n_leaf_tris;          /* original triangle indices in `flatten` order (BIH.hs:50-52) */
@@ -262,7 +265,7 @@ orc_scene *orc_scene_from_arrays(const float *v9, const int *mat_idx, int n_tris
 void orc_free_scene(orc_scene *s)
 {
     if (!s) return;
-    free(s->tris); free(s->mats); free(s->nodes); free(s->leaf_tris); free(s);
+    free(s->tris); free(s->mats); free(s->nodes); free(s->leaf_tris); free(s->spheres); free(s);
 }
 const char *orc_error(orc_scene *s) { return s->err; }
 int orc_n_tris(orc_scene *s) { return s->n_tris; }
@@ -592,11 +595,64 @@ static isect intersect_bih_rec(const orc_scene *s, bounds bbox, int node, ray r,
     if (ir) return intersect_bih_rec(s, right, n->right, r, cn);  /* BIH.hs:118 */
     return none;
 }
-/* BIH.hs:101-102 */
+/* EXTENSION (the reference has no sphere): double-sided analytic sphere with the conventions of mollerTrumbore --
+ * eps = 1e-4, point = o + t *^ d, dist = norm (point - o).  Restates the semantics fixed in include/sqt.h. */
+static inline isect ray_sphere(ray r, const sphere *sp, int surface_index)
+{
+    isect none = { 0, { 0, 0, 0 }, 0, -1 };
+    const float eps = 0.0001f;
+    v3 oc = vsub(r.o, sp->c);
+    float A = vdot(r.d, r.d);
+    float B = vdot(oc, r.d);
+    float C = vdot(oc, oc) - sp->r * sp->r;
+    float disc = B * B - A * C;
+    if (!(disc >= 0)) return none;
+    float sq = sqrtf(disc);
+    float t0 = (-B - sq) / A, t1 = (-B + sq) / A;
+    float t = t0 > eps ? t0 : t1;
+    if (!(t > eps)) return none;
+    isect out;
+    out.hit = 1;
+    out.point = vadd(r.o, vscale(t, r.d));
+    out.dist = vnorm(vsub(out.point, r.o));
+    out.tri = surface_index;
+    return out;
+}
+/* candidates in order [accelerated hit, sphere 0, sphere 1, ...], minimumBy (comparing dist): the first minimal wins */
+static inline isect with_spheres(const orc_scene *s, ray r, isect best)
+{
+    for (int k = 0; k < s->n_spheres; k++) {
+        isect h = ray_sphere(r, &s->spheres[k], s->n_tris + k);
+        if (!h.hit) continue;
+        if (!best.hit || cmp_gt(best.dist, h.dist)) best = h;
+    }
+    return best;
+}
+/* BIH.hs:101-102 (+ the sphere extension) */
 static inline isect intersect_bih(const orc_scene *s, ray r, orc_counters *cn)
 {
     if (cn) cn->rays++;
-    return intersect_bih_rec(s, s->root, 0, r, cn);
+    return with_spheres(s, r, intersect_bih_rec(s, s->root, 0, r, cn));
+}
+/* material and un-normalised geometric normal of the surface an intersection lies on */
+static inline const material *surface_material(const orc_scene *s, const isect *in)
+{
+    return in->tri >= s->n_tris ? &s->mats[s->spheres[in->tri - s->n_tris].mat] : &s->mats[s->tris[in->tri].mat];
+}
+static inline v3 surface_normal(const orc_scene *s, const isect *in)
+{
+    if (in->tri >= s->n_tris) return vsub(in->point, s->spheres[in->tri - s->n_tris].c);
+    return tri_normal(&s->tris[in->tri]);
+}
+void orc_set_spheres(orc_scene *s, const float *s5, int n)      /* rows (cx, cy, cz, r, material index) */
+{
+    free(s->spheres);
+    s->spheres = (sphere *)malloc((size_t)(n ? n : 1) * sizeof(sphere));
+    s->n_spheres = n;
+    for (int k = 0; k < n; k++) {
+        sphere sp = { V(s5[5 * k], s5[5 * k + 1], s5[5 * k + 2]), s5[5 * k + 3], (int)s5[5 * k + 4] };
+        s->spheres[k] = sp;
+    }
 }
 
 /* ============================================================ thread pool */
@@ -639,7 +695,7 @@ static void batch_chunk(void *p, int64_t lo, int64_t hi, int tid)
     for (int64_t i = lo; i < hi; i++) {
         ray r = { V(b->org[3 * i], b->org[3 * i + 1], b->org[3 * i + 2]), V(b->dir[3 * i], b->dir[3 * i + 1], b->dir[3 * i + 2]) };
         isect h;
-        if (b->naive) { if (cn) cn->rays++; h = naive_intersect(b->s, r, cn); }
+        if (b->naive) { if (cn) cn->rays++; h = with_spheres(b->s, r, naive_intersect(b->s, r, cn)); }
         else h = intersect_bih(b->s, r, cn);
         b->tri_out[i] = h.hit ? h.tri : -1;
         if (b->dist_out) b->dist_out[i] = h.hit ? h.dist : 0.0f;
@@ -818,8 +874,7 @@ static v3 raytrace(const render_ctx *rc, uint64_t stream, ray r, int bounces, or
     if (bounces > rc->p.max_depth - 1) return black;               /* reference: bounces > 2 */
     isect in = intersect_bih(rc->s, r, cn);
     if (!in.hit) return black;
-    const triangle *tri = &rc->s->tris[in.tri];
-    const material *m = &rc->s->mats[tri->mat];
+    const material *m = surface_material(rc->s, &in);
     v3 next = black;
     if (bounces + 1 <= rc->p.max_depth - 1) {                      /* lazy: newRay only forced if traced */
         float x = random_r01(draw_word(rc->p.seed, stream, (uint32_t)bounces));
@@ -827,13 +882,13 @@ static v3 raytrace(const render_ctx *rc, uint64_t stream, ray r, int bounces, or
         if (m->reflective < x) {                                   /* Lib.hs:157 scatterRay, Lib.hs:166-172 */
             float v = random_r01(draw_word(rc->p.seed, stream, (uint32_t)bounces + 1));
             v3 nd = random_vector(x, v, rc->p.trig);
-            v3 n = tri_normal(tri);
+            v3 n = surface_normal(rc->s, &in);
             float old = hs_signum(vdot(r.d, n));
             float nw = hs_signum(vdot(nd, n));
             nr.o = in.point;
             nr.d = (old == nw) ? vneg(nd) : nd;
         } else {                                                   /* Lib.hs:176-181 */
-            v3 dn = vnormalize(tri_normal(tri));
+            v3 dn = vnormalize(surface_normal(rc->s, &in));
             v3 di = r.d;
             nr.o = in.point;
             nr.d = vsub(di, vscale(2 * vdot(dn, di), dn));
@@ -851,7 +906,7 @@ static v3 raycast(const render_ctx *rc, ray r, orc_counters *cn)
     const v3 black = V(0, 0, 0);
     isect in = intersect_bih(rc->s, r, cn);
     if (!in.hit) return black;
-    const material *m = &rc->s->mats[rc->s->tris[in.tri].mat];
+    const material *m = surface_material(rc->s, &in);
     v3 light = V(0, 3, -1);
     ray shadow = { in.point, vsub(light, in.point) };              /* a `to` b = Ray a (b - a) */
     float dl = vnorm(vsub(in.point, light));

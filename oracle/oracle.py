@@ -35,6 +35,7 @@ def lib():
         for f in ("orc_n_tris", "orc_n_mats", "orc_n_nodes", "orc_height", "orc_longest_leaf", "orc_n_leaves", "orc_make_bih"):
             getattr(L, f).restype = C.c_int
             getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_set_spheres.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_get_tris.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_get_mats.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_export_bih.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -133,6 +134,11 @@ class Scene:
         m = np.zeros((lib().orc_n_mats(self.h), 8), np.float32)
         lib().orc_get_mats(self.h, _p(m))
         return m
+
+    def set_spheres(self, spheres):
+        """EXTENSION (no reference counterpart): rows (cx, cy, cz, radius, material index)."""
+        a = np.ascontiguousarray(np.asarray(spheres, np.float32).reshape(-1, 5))
+        lib().orc_set_spheres(self.h, _p(a) if len(a) else None, len(a))
 
     def make_bih(self):
         lib().orc_make_bih(self.h)

@@ -458,7 +458,7 @@ struct sqt_ctx {
     // scene
     bool has_scene = false;
     SceneView sc = {};
-    float4 *d_nodes = nullptr, *d_tris = nullptr, *d_mats = nullptr, *d_leaves = nullptr;
+    float4 *d_nodes = nullptr, *d_tris = nullptr, *d_mats = nullptr, *d_leaves = nullptr, *d_spheres = nullptr;
     int leaf_cull = 1;
     int terminate_on_black_ok = 0;
     uint32_t tree_height = 0;
@@ -543,8 +543,8 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
 }
 
 static void free_scene(sqt_ctx *c) {
-    cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_mats); cudaFree(c->d_leaves);
-    c->d_nodes = c->d_tris = c->d_mats = c->d_leaves = nullptr; c->has_scene = false;
+    cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_mats); cudaFree(c->d_leaves); cudaFree(c->d_spheres);
+    c->d_nodes = c->d_tris = c->d_mats = c->d_leaves = c->d_spheres = nullptr; c->has_scene = false;
 }
 
 extern "C" int sqt_destroy(sqt_ctx *c) {
@@ -603,6 +603,27 @@ extern "C" int sqt_upload_scene(sqt_ctx *ctx, const sqt_scene_desc *s) {
     v.n_branches = n_br; v.n_tris = s->n_tris; v.n_mats = s->n_mats;
     v.root_is_leaf = (s->nodes[0].b & SQT_NODE_LEAF) ? 1u : 0u;
     ctx->sc = v; ctx->has_scene = true; ctx->terminate_on_black_ok = tob; ctx->tree_height = height;
+    return SQT_OK;
+}
+
+// extension: analytic spheres (include/sqt.h)
+extern "C" int sqt_upload_spheres(sqt_ctx *ctx, const sqt_sphere *sp, uint32_t n) {
+    if (!ctx) return SQT_E_INVALID;
+    if (!ctx->has_scene) return fail(ctx, SQT_E_NO_SCENE, "sqt_upload_spheres before sqt_upload_scene");
+    if (n && !sp) return fail(ctx, SQT_E_INVALID, "spheres is NULL");
+    if ((uint64_t)ctx->sc.n_tris + n >= (1u << 27)) return fail(ctx, SQT_E_UNSUPPORTED, "too many surfaces");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<float4> ds((size_t)2 * (n ? n : 1));
+    for (uint32_t k = 0; k < n; ++k) {
+        if (sp[k].material >= ctx->sc.n_mats) return fail(ctx, SQT_E_INVALID, "sphere %u: material %u out of range", k, sp[k].material);
+        if (!(sp[k].radius > 0.0f)) return fail(ctx, SQT_E_INVALID, "sphere %u: radius must be positive", k);
+        ds[2 * k] = make_float4(sp[k].center[0], sp[k].center[1], sp[k].center[2], sp[k].radius);
+        ds[2 * k + 1] = make_float4(u2f(sp[k].material), 0.0f, 0.0f, 0.0f);
+    }
+    cudaFree(ctx->d_spheres); ctx->d_spheres = nullptr;
+    CU(cudaMalloc(&ctx->d_spheres, ds.size() * sizeof(float4)));
+    CU(cudaMemcpy(ctx->d_spheres, ds.data(), ds.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    ctx->sc.spheres = ctx->d_spheres; ctx->sc.n_spheres = n;
     return SQT_OK;
 }
 

@@ -83,6 +83,8 @@ struct SceneView {
     const float4 *leaves;    // 2 float4 per leaf
     const float4 *tris;      // 3 float4 per triangle: (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z, mat, orig, pad)
     const float4 *mats;      // 3 float4 per material: (refl, surf.rgb) (emissive, emit.rgb) (ec.rgb, flags)
+    const float4 *spheres;   // extension: 2 float4 per sphere: (center.xyz, radius) (material bits, -, -, -)
+    uint32_t n_spheres;
     float root_lo[3], root_hi[3];
     uint32_t n_branches, n_tris, n_mats;
     uint32_t root_is_leaf;   // tree = Leaf: no box test at all (BIH.hs:105)
@@ -243,6 +245,48 @@ struct TravLane {
     uint32_t *stack;            // kStackWords words of lane-private (local) memory, owned by the caller
 };
 
+// ---- extension: analytic spheres (no reference counterpart; semantics restated in oracle/oracle.c) ----------------
+// oc = o - c ; A = d.d ; B = oc.d ; C = oc.oc - r*r ; disc = B*B - A*C ; disc < 0 -> Nothing
+// t0 = (-B - sqrt disc)/A ; t1 = (-B + sqrt disc)/A ; t = first of t0, t1 that is > eps (1e-4, as mollerTrumbore)
+// point = o + t *^ d ; dist = norm (point - o)     -- same conventions as Geometry.hs:134,141
+SQT_HD bool ray_sphere(const float4 &s0, const Ray &r, float &t_out, float &dist_out) {
+    const float eps = 0.0001f;
+    const float ocx = XSUB(r.ox, s0.x), ocy = XSUB(r.oy, s0.y), ocz = XSUB(r.oz, s0.z);
+    const float A = dot3(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
+    const float B = dot3(ocx, ocy, ocz, r.dx, r.dy, r.dz);
+    const float C = XSUB(dot3(ocx, ocy, ocz, ocx, ocy, ocz), XMUL(s0.w, s0.w));
+    const float disc = XSUB(XMUL(B, B), XMUL(A, C));
+    if (!(disc >= 0.0f)) return false;
+    const float sq = XSQRT(disc);
+    const float t0 = XDIV(XSUB(-B, sq), A), t1 = XDIV(XADD(-B, sq), A);
+    const float t = t0 > eps ? t0 : t1;
+    if (!(t > eps)) return false;
+    const float px = XADD(r.ox, XMUL(t, r.dx)), py = XADD(r.oy, XMUL(t, r.dy)), pz = XADD(r.oz, XMUL(t, r.dz));
+    const float ex = XSUB(px, r.ox), ey = XSUB(py, r.oy), ez = XSUB(pz, r.oz);
+    t_out = t;
+    dist_out = XSQRT(dot3(ex, ey, ez, ex, ey, ez));
+    return true;
+}
+
+// The BIH part of a ray is finished with `cur`: fold in the spheres (candidates in order [BIH hit, sphere 0, sphere 1, ..],
+// minimumBy (comparing dist): an earlier candidate wins ties), then the ray is ST_DONE.  Surface n_tris + k = sphere k.
+SQT_HD void finish_ray(const SceneView &sc, TravLane &L) {
+    for (uint32_t k = 0; k < sc.n_spheres; ++k) {
+        const float4 s0 = SQT_LDG4(sc.spheres + 2 * (size_t)k);
+        float t, dist;
+        if (ray_sphere(s0, L.r, t, dist)) {
+            if (L.cur.tri < 0 || cmp_gt(L.cur.dist, dist)) { L.cur.tri = (int)(sc.n_tris + k); L.cur.t = t; L.cur.dist = dist; }
+        }
+    }
+    L.state = ST_DONE;
+}
+
+// material index and (un-normalised) geometric normal of surface `idx` at the hit point (hx,hy,hz)
+SQT_HD uint32_t surface_material(const SceneView &sc, int idx) {
+    if ((uint32_t)idx >= sc.n_tris) return f2u(SQT_LDG4(sc.spheres + 2 * (size_t)((uint32_t)idx - sc.n_tris) + 1).x);
+    return f2u(SQT_LDG4(sc.tris + 3 * (size_t)idx + 2).y);
+}
+
 // intersectBIH b = intersectBIH' (bounds b) (tree b)   (BIH.hs:101-102)
 template <bool COUNT>
 SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
@@ -251,15 +295,15 @@ SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
     L.sp = 0;
     if (sc.root_is_leaf) {                       // tree = Leaf: no box test at all (BIH.hs:105)
         L.child = 0u; L.i = (int)sc.n_tris - 1;
-        L.state = sc.n_tris ? ST_LEAF : ST_DONE;
         if (COUNT) cn->tri_tests += sc.n_tris;
+        if (sc.n_tris) L.state = ST_LEAF; else finish_ray(sc, L);
         return;
     }
     L.dfx = XRCP(L.r.dx); L.dfy = XRCP(L.r.dy); L.dfz = XRCP(L.r.dz);
     L.safe = finite_f(L.dfx) && finite_f(L.dfy) && finite_f(L.dfz) && finite_f(L.r.dx) && finite_f(L.r.dy) &&
              finite_f(L.r.dz) && finite_f(L.r.ox) && finite_f(L.r.oy) && finite_f(L.r.oz);
     if (!slab_exact(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], L.r, L.dfx,
-                    L.dfy, L.dfz)) { L.state = ST_DONE; return; }          // BIH.hs:112 at the root
+                    L.dfy, L.dfz)) { finish_ray(sc, L); return; }          // BIH.hs:112 at the root
     L.sgn = (L.r.dx > 0.0f ? 1u : 0u) | (L.r.dy > 0.0f ? 2u : 0u) | (L.r.dz > 0.0f ? 4u : 0u);
     { const float d1 = fabsf(L.r.dx) + fabsf(L.r.dy) + fabsf(L.r.dz); L.dfac = d1 * (1.0f + d1); }
     L.child = 0u; L.meta = 0u; L.state = ST_DESC;
@@ -367,7 +411,7 @@ SQT_HD void tri_step(const SceneView &sc, TravLane &L, Counters *cn) {
 // the stack is empty (-> ST_DONE).  Pops that only merge or propagate are a handful of instructions each.
 SQT_HD void ret_step(const SceneView &sc, TravLane &L) {
     for (;;) {
-        if (L.sp == 0) { L.state = ST_DONE; return; }
+        if (L.sp == 0) { finish_ray(sc, L); return; }
         const uint32_t w0 = L.stack[L.sp - 3], w1 = L.stack[L.sp - 2], w2 = L.stack[L.sp - 1];
         L.sp -= 3;
         if (w2 & kPhaseB) {                                                 // far subtree returned: min' near far
@@ -515,15 +559,21 @@ SQT_HD float hs_signum(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : x
 // drew x = draw j (scatter iff reflective < x) and, for a scatter, v = draw j+1: scatter reuses x as the
 // azimuth draw and takes v as the polar draw.  Returns the new ray; origin = intersectPoint.
 SQT_HD Ray bounce_ray(const SceneView &sc, const Ray &in, int tri, float t, bool scatter, float x, float v) {
-    const float4 *p = sc.tris + 3 * (size_t)tri;
-    const float4 a0 = SQT_LDG4(p), a1 = SQT_LDG4(p + 1), a2 = SQT_LDG4(p + 2);
-    const float e1x = a0.w, e1y = a1.x, e1z = a1.y, e2x = a1.z, e2y = a1.w, e2z = a2.x;
-    // normal = (b - a) `cross` (c - a)   Geometry.hs:79-80
-    const float nx = XSUB(XMUL(e1y, e2z), XMUL(e1z, e2y));
-    const float ny = XSUB(XMUL(e1z, e2x), XMUL(e1x, e2z));
-    const float nz = XSUB(XMUL(e1x, e2y), XMUL(e1y, e2x));
     Ray out;
     out.ox = XADD(in.ox, XMUL(t, in.dx)); out.oy = XADD(in.oy, XMUL(t, in.dy)); out.oz = XADD(in.oz, XMUL(t, in.dz));
+    float nx, ny, nz;
+    if ((uint32_t)tri >= sc.n_tris) {           // extension: sphere, normal = intersectPoint - center
+        const float4 s0 = SQT_LDG4(sc.spheres + 2 * (size_t)((uint32_t)tri - sc.n_tris));
+        nx = XSUB(out.ox, s0.x); ny = XSUB(out.oy, s0.y); nz = XSUB(out.oz, s0.z);
+    } else {
+        const float4 *p = sc.tris + 3 * (size_t)tri;
+        const float4 a0 = SQT_LDG4(p), a1 = SQT_LDG4(p + 1), a2 = SQT_LDG4(p + 2);
+        const float e1x = a0.w, e1y = a1.x, e1z = a1.y, e2x = a1.z, e2y = a1.w, e2z = a2.x;
+        // normal = (b - a) `cross` (c - a)   Geometry.hs:79-80
+        nx = XSUB(XMUL(e1y, e2z), XMUL(e1z, e2y));
+        ny = XSUB(XMUL(e1z, e2x), XMUL(e1x, e2z));
+        nz = XSUB(XMUL(e1x, e2y), XMUL(e1y, e2x));
+    }
     if (scatter) {                              // scatterRay, Lib.hs:166-172 ; randomVector Lib.hs:192-198
         const float th = XMUL(6.28318530717958647692f, x);             // 2 * pi * u
         const float ph = sqt_acos(XSUB(XMUL(2.0f, v), 1.0f));

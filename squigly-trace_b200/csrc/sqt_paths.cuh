@@ -149,8 +149,7 @@ SQT_HD void path_regen(const SceneView &sc, const RenderParams &p, const RoundIn
             }
         }
         // ---- shade the hit of bounce j (raytrace, Lib.hs:127-137); L.r is the ray that produced it
-        const float4 *tp = sc.tris + 3 * (size_t)htri;
-        const uint32_t mat = f2u(SQT_LDG4(tp + 2).y);
+        const uint32_t mat = surface_material(sc, htri);
         pm[q.j] = (uint16_t)mat;
         const float4 *mp = sc.mats + 3 * (size_t)mat;
         const float4 m0 = SQT_LDG4(mp);
@@ -223,7 +222,8 @@ struct BatchPolicy {
             in_flight = false;
             st.rays += 1;
             const bool hit = L.cur.tri >= 0;
-            tri_out[idx] = hit ? (int)f2u(SQT_LDG4(sc.tris + 3 * (size_t)L.cur.tri + 2).z) : -1;
+            // triangles report their position in the parsed list, sphere k reports n_tris + k
+            tri_out[idx] = !hit ? -1 : ((uint32_t)L.cur.tri >= sc.n_tris ? L.cur.tri : (int)f2u(SQT_LDG4(sc.tris + 3 * (size_t)L.cur.tri + 2).z));
             if (dist_out) dist_out[idx] = hit ? L.cur.dist : 0.0f;
             if (point_out) {
                 point_out[3 * idx] = hit ? XADD(L.r.ox, XMUL(L.cur.t, L.r.dx)) : 0.0f;
@@ -295,7 +295,7 @@ struct CastPolicy {
     SQT_HD void finish(const SceneView &sc, bool lit) {
         float cr = 0.0f, cg = 0.0f, cb = 0.0f;
         if (lit) {
-            const uint32_t mat = f2u(SQT_LDG4(sc.tris + 3 * (size_t)htri + 2).y);
+            const uint32_t mat = surface_material(sc, htri);
             const float4 m0 = SQT_LDG4(sc.mats + 3 * (size_t)mat);
             const float kk = XDIV(2.0f, dl);                        // (2 / distanceToLight) *^ surfColor
             cr = XMUL(kk, m0.y); cg = XMUL(kk, m0.z); cb = XMUL(kk, m0.w);

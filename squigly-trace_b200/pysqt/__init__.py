@@ -27,7 +27,7 @@ SQT_COMM_ID_BYTES = 128
 ABI_SYMBOLS = [
     "sqt_abi_version", "sqt_create", "sqt_destroy", "sqt_last_error", "sqt_upload_scene", "sqt_intersect_batch",
     "sqt_render", "sqt_render_resident", "sqt_download_image", "sqt_tone_map", "sqt_comm_unique_id", "sqt_comm_init",
-    "sqt_comm_init_all", "sqt_render_group", "sqt_measure_fp32_peak", "sqt_measure_l2_bandwidth", "sqt_device_info", "sqt_set_option",
+    "sqt_comm_init_all", "sqt_render_group", "sqt_measure_fp32_peak", "sqt_measure_l2_bandwidth", "sqt_device_info", "sqt_set_option", "sqt_upload_spheres",
 ]
 
 
@@ -77,6 +77,7 @@ class Stats(C.Structure):
 
 NODE_DT = np.dtype([("lmax", "<f4"), ("rmin", "<f4"), ("a", "<u4"), ("b", "<u4")])
 TRI_DT = np.dtype([("v0", "<f4", 3), ("e1", "<f4", 3), ("e2", "<f4", 3), ("material", "<u4"), ("orig_index", "<u4"), ("pad", "<u4")])
+SPHERE_DT = np.dtype([("center", "<f4", 3), ("radius", "<f4"), ("material", "<u4"), ("pad", "<u4", 3)])
 MAT_DT = np.dtype([("reflective", "<f4"), ("surf_color", "<f4", 3), ("emissive", "<f4"), ("emit_color", "<f4", 3)])
 assert NODE_DT.itemsize == 16 and TRI_DT.itemsize == 48 and MAT_DT.itemsize == 32
 
@@ -114,6 +115,7 @@ def b200():
         L.sqt_measure_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.sqt_measure_l2_bandwidth.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.sqt_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.sqt_upload_spheres.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.sqt_device_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p]
         for name in ABI_SYMBOLS:
             if name not in ("sqt_last_error",):
@@ -311,6 +313,13 @@ class Context:
         out = np.zeros(mean_rgb.shape, np.uint8)
         self._ck(self.L.sqt_tone_map(self.h, _p(mean_rgb), mean_rgb.size // 3, _p(out)), "sqt_tone_map")
         return out
+
+    def upload_spheres(self, spheres):
+        """spheres: rows (cx, cy, cz, radius, material) -- extension, see include/sqt.h"""
+        a = np.zeros(len(spheres), SPHERE_DT)
+        for i, (cx, cy, cz, r, m) in enumerate(spheres):
+            a[i]["center"] = (cx, cy, cz); a[i]["radius"] = r; a[i]["material"] = int(m)
+        self._ck(self.L.sqt_upload_spheres(self.h, _p(a) if len(a) else None, len(a)), "sqt_upload_spheres")
 
     def set_leaf_cull(self, on):
         self._ck(self.L.sqt_set_option(self.h, 1, 1 if on else 0), "sqt_set_option")

@@ -27,6 +27,7 @@ def emu_lib():
         E.emu_height.restype = C.c_int
         E.emu_height.argtypes = [C.c_void_p]
         E.emu_set_leaf_cull.argtypes = [C.c_void_p, C.c_int]
+        E.emu_set_spheres.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
         E.emu_intersect_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         E.emu_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _EMU = E
@@ -62,6 +63,13 @@ class Emu:
 
     def set_leaf_cull(self, on):
         emu_lib().emu_set_leaf_cull(self.h, 1 if on else 0)
+
+    def set_spheres(self, spheres):
+        a = np.zeros(len(spheres), pysqt.SPHERE_DT)
+        for i, (cx, cy, cz, r, m) in enumerate(spheres):
+            a[i]["center"] = (cx, cy, cz); a[i]["radius"] = r; a[i]["material"] = int(m)
+        self._spheres = a
+        emu_lib().emu_set_spheres(self.h, _p(a) if len(a) else None, len(a))
 
     def render(self, cam12, params, rank=0, world=1):
         acc = np.zeros((params.rows, params.cols, 3), np.float32)

@@ -15,7 +15,7 @@ using namespace sqt;
 
 struct emu_scene {
     DeviceLayout lay;
-    std::vector<float4> tris;
+    std::vector<float4> tris, spheres;
     SceneView view;
     std::string err;
 };
@@ -52,6 +52,14 @@ const char *emu_error(emu_scene *s) { return s->err.c_str(); }
 void emu_free(emu_scene *s) { delete s; }
 int emu_height(emu_scene *s) { return (int)s->lay.height; }
 void emu_set_leaf_cull(emu_scene *s, int on) { s->view.leaf_cull = on ? 1u : 0u; }
+void emu_set_spheres(emu_scene *s, const sqt_sphere *sp, unsigned n) {
+    s->spheres.assign((size_t)2 * (n ? n : 1), float4{0, 0, 0, 0});
+    for (unsigned k = 0; k < n; ++k) {
+        s->spheres[2 * k] = float4{sp[k].center[0], sp[k].center[1], sp[k].center[2], sp[k].radius};
+        s->spheres[2 * k + 1] = float4{u2f(sp[k].material), 0, 0, 0};
+    }
+    s->view.spheres = s->spheres.data(); s->view.n_spheres = n;
+}
 void emu_set_sbuf_budget(long long bytes) { sbuf_budget = bytes; }
 
 void emu_intersect_batch(emu_scene *s, const float *org, const float *dir, long long n, int *tri_out, float *dist_out,

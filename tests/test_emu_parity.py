@@ -94,3 +94,34 @@ def test_upload_validation_errors(host_scene):
     tris = host_scene.tris.copy(); tris["material"][5] = 99
     d = host_scene.desc(); d.tris = tris.ctypes.data
     assert "material 99" in err_of(d)
+
+
+SPHERES = [(0.8, 0.5, -1.2, 0.6, 5), (-0.9, 1.0, 0.3, 0.45, 1), (0.0, -0.5, 1.2, 0.3, 3), (0.0, 3.0, 0.5, 0.25, 2)]
+
+
+def test_sphere_extension(host_scene, camera):
+    """Analytic spheres (north-star extension without a reference counterpart): device logic vs the oracle's
+    restatement of the same semantics -- mirror, diffuse and emissive spheres, one of them outside the BIH bounds."""
+    e = Emu(host_scene)
+    osc = O.Scene.load(pysqt.ROOT + "/data/scene.obj", pysqt.ROOT + "/data")
+    osc.make_bih()
+    e.set_spheres(SPHERES); osc.set_spheres(SPHERES)
+    org, dirs = O.make_rays(O.make_params(160, 160, 1), camera)
+    o2, d2 = random_rays(40000, 9)
+    org = np.concatenate([org, o2]); dirs = np.concatenate([dirs, d2])
+    want = osc.intersect_batch(org, dirs)
+    assert_same_hits(e.intersect_batch(org, dirs), want, "spheres")
+    assert (want[0] >= osc.n_tris).sum() > 1000
+    naive = osc.intersect_batch(org[:4000], dirs[:4000], naive=True)
+    assert np.array_equal(bits(naive[1]), bits(want[1][:4000]))
+    for depth, mode in ((3, 0), (8, 0), (3, 1)):
+        got = e.render(camera, pysqt.make_params(72, 48, 5, max_depth=depth, seed=3, mode=mode))
+        ref = osc.render(camera, O.make_params(72, 48, 5, max_depth=depth, seed=3, trig=1, mode=mode))
+        assert np.array_equal(bits(got["accum"]), bits(ref["accum"])) and np.array_equal(got["rgb8"], ref["rgb8"])
+    e.set_spheres([])
+    assert_same_hits(e.intersect_batch(org[:5000], dirs[:5000]), O.Scene.intersect_batch(_plain(osc), org[:5000], dirs[:5000]), "spheres removed")
+
+
+def _plain(osc):
+    osc.set_spheres([])
+    return osc

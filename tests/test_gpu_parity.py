@@ -314,6 +314,33 @@ def test_synthetic_cornell_render_bit_exact(gpu_ctx, camera):
     assert np.array_equal(bits(out["accum"]), bits(ref["accum"]))
 
 
+def test_sphere_extension_bit_exact(host_scene, camera):
+    """Analytic spheres (north-star extension; semantics in include/sqt.h, restated by the oracle)."""
+    spheres = [(0.8, 0.5, -1.2, 0.6, 5), (-0.9, 1.0, 0.3, 0.45, 1), (0.0, -0.5, 1.2, 0.3, 3), (0.0, 3.0, 0.5, 0.25, 2)]
+    osc = O.Scene.load(pysqt.ROOT + "/data/scene.obj", pysqt.ROOT + "/data")
+    osc.make_bih()
+    osc.set_spheres(spheres)
+    ctx = pysqt.Context(0)
+    ctx.upload(host_scene)
+    ctx.upload_spheres(spheres)
+    org, dirs = O.make_rays(O.make_params(300, 300, 1), camera)
+    o2, d2 = random_rays(200000, 9)
+    org = np.concatenate([org, o2]); dirs = np.concatenate([dirs, d2])
+    want = osc.intersect_batch(org, dirs)
+    assert_same_hits(ctx.intersect_batch(org, dirs), want, "spheres")
+    assert (want[0] >= osc.n_tris).sum() > 5000
+    for depth, mode in ((3, 0), (8, 0), (3, 1)):
+        out = ctx.render(camera, pysqt.make_params(96, 64, 6, max_depth=depth, seed=3, mode=mode))
+        ref = osc.render(camera, O.make_params(96, 64, 6, max_depth=depth, seed=3, trig=1, mode=mode))
+        assert np.array_equal(bits(out["accum"]), bits(ref["accum"])) and np.array_equal(out["rgb8"], ref["rgb8"])
+    bad = pysqt.np.zeros(1, pysqt.SPHERE_DT); bad[0]["radius"] = 1.0; bad[0]["material"] = 99
+    assert ctx.L.sqt_upload_spheres(ctx.h, bad.ctypes.data, 1) == 1 and "material" in ctx.last_error()
+    ctx.upload_spheres([])
+    plain = O.Scene.load(pysqt.ROOT + "/data/scene.obj", pysqt.ROOT + "/data"); plain.make_bih()
+    assert_same_hits(ctx.intersect_batch(org[:20000], dirs[:20000]), plain.intersect_batch(org[:20000], dirs[:20000]), "spheres removed")
+    ctx.close()
+
+
 # ------------------------------------------------------------------ full-size, size-independent properties
 def test_full_size_properties_1080p(gpu_ctx, host_scene, oracle_scene, camera):
     """BASELINE config 2 geometry (1920x1080, depth 8) at a reduced spp the oracle cannot follow in full:
