@@ -34,7 +34,7 @@ struct DeviceStats {
     unsigned long long branch_visits, child_box_tests, tri_tests, leaves_culled;
     unsigned long long mt_pass_a, mt_pass_u, mt_pass_v, mt_accept;
     unsigned long long n_hit;           // length of the pixel list k_primary builds
-    unsigned long long work_next[64];   // dynamic work counters of k_paths, one per round
+    unsigned long long work_next[256];  // dynamic work counters of the path kernels, one per round
 };
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -822,7 +822,7 @@ static int enqueue_render(sqt_ctx *ctx, const RenderParams &d, bool count, uint3
         rd.n_slots = nwork; rd.slot_stride = nwork;
         rd.log2_s = round_log2_s(nwork, k1 - k0 > 0 ? k1 - k0 : 1, ctx->sbuf_budget);
         const int S = 1 << rd.log2_s;
-        if ((k1 - k0 + S - 1) / S > 64) return fail(ctx, SQT_E_UNSUPPORTED, "more than 64 sample rounds (raise SQT_SBUF_MB)");
+        if ((k1 - k0 + S - 1) / S > 256) return fail(ctx, SQT_E_UNSUPPORTED, "more than 256 sample rounds (raise SQT_SBUF_MB)");
         const long long sbytes = nwork * (long long)S * 12ll;
         rc = ensure_sbuf(ctx, sbytes); if (rc) return rc;
         rd.sbuf = ctx->d_sbuf;
