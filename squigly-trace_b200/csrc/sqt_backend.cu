@@ -3,11 +3,14 @@
 // Kernels
 //   k_intersect_batch  : one lane per ray, grid-stride; batched Scene.intersect (Geometry.hs:64 / BIH.hs:101)
 //   k_primary          : one lane per pixel; makeRay (Lib.hs:107-114) + closest hit, cached per pixel
-//   k_paths            : persistent lanes, dynamic pixel fetch, path regeneration (sqt_paths.cuh)
+//   k_paths_pool       : the integrator: every warp owns a pool of 32*K rays in shared memory and regroups them by
+//                        the kind of step they need (default)
+//   k_paths            : the integrator with one ray per lane and warp-synchronous phases (SQT_POOL=0)
+//   k_accumulate       : adds a round's samples to the per-pixel sums in sample order (Lib.hs:88)
 //   k_raycast          : --cast mode (Lib.hs:141-151)
 //   k_tonemap          : mean + rgbFloatToPixelRGB (Lib.hs:88-104)
 //   k_fp32_peak, k_l2_read : roofline denominators measured on the device
-// Host side: context, scene upload (derives the 48-byte branch records from the 16-byte boundary nodes),
+// Host side: context, scene upload (derives the 64-byte branch and 32-byte leaf records from the 16-byte boundary nodes),
 // NCCL group (dlopen'ed), CUDA-event timing of every launch.
 //
 // There is no CPU fallback in this file: every entry point needs a compute-capability-10.x device.

@@ -11,10 +11,10 @@
 // (sqt_core.cuh).  Lanes are independent, so any schedule yields the same per-lane results; tests/emu runs
 // each lane to completion on the host with the same functions.
 //
-// Integrator layout: one lane owns one pixel at a time and runs its samples k = k0..k1-1 in order, so the
-// per-pixel radiance sum is the reference's sequential `sum = foldl (+) 0` (Lib.hs:88).  A lane whose path
-// ends (miss, depth cut, black surface) starts its next sample -- or fetches its next pixel -- right away
-// (path regeneration), so lanes re-enter the traversal with a live ray.
+// Integrator layout: the work item is one SAMPLE of one pixel; a frame is rendered in rounds of S samples per pixel
+// whose radiances go to a sample buffer and are then added to the per-pixel sums strictly in sample order
+// (accumulate_slot), so the sum is the reference's sequential `sum = foldl (+) 0` (Lib.hs:88).  A lane (or pool slot)
+// whose path ends (miss, depth cut, black surface) fetches its next sample right away (path regeneration).
 #pragma once
 #include "sqt_core.cuh"
 
