@@ -311,17 +311,16 @@ SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
 
 // Entering Leaf `L.child` (index into the leaf array) with `count` triangles (BIH.hs:105-109).
 //
-// Conservative leaf culling (not in the reference; exact by a forward error bound).  A triangle test can
-// only return Just if |a| >= 1e-4 and the computed u, v, u+v pass their guards and t > 1e-4
-// (Geometry.hs:117-142).  With binary32 unit roundoff eps = 2^-24 and the triangle spanned by (v0, e1, e2),
-// the computed u, v, t differ from their exact values by at most c*eps*|d|*E*(|s|+E)/|a| (E = longest edge,
-// s = origin - v0, c < 8: every numerator is a 3-term dot of a 2-term cross).  Hence an accepted hit lies,
-// in exact arithmetic, within  2*c*eps/1e-4 * |d|*(1+|d|)*E^2*(|s|+E) < 0.01*|d|(1+|d|)E^2(|s|+E)  of the
-// triangle, with the ray origin at most that far behind it.  The leaf is skipped only if the ray misses the
-// leaf's tight box enlarged by THREE times that bound (K = 0.03, norms over-estimated by 1-norms) plus
-// 1e-4 + 2^-20*max|coordinate|: no skipped triangle could have been accepted, so the traversal result is
-// bit-identical (tests: culling on/off agree on every ray; both agree with the oracle).
-// Rays with a zero/denormal/non-finite direction component (`safe` false) are never culled.
+// Conservative leaf culling (not in the reference; exact by a forward error bound, derivation in DESIGN.md section 5).
+// A triangle test can only return Just if |a| >= 1e-4 and the computed u, v, u+v pass their guards and t > 1e-4
+// (Geometry.hs:117-142).  With eps = 2^-24, E the longest edge in the leaf and s = origin - v0, every numerator is
+// a 3-term dot of a 2-term cross and is off by at most 12*eps*|d|*E*(|s|_1 + E); after the division by |a| >= 1e-4
+// an accepted hit lies, in exact arithmetic, within 0.0143*|d|*E^2*(|s|_1+E) of the triangle (origin at most that
+// far behind it).  The leaf is skipped only if the ray misses the leaf's tight box enlarged by
+// 0.03*|d|_1*(1+|d|_1)*E^2*(|s|_1+E)  (>= 2x the bound, 1-norm over-estimates)  +  1e-4 + 2^-20*(max|coord| + |s|_1):
+// no skipped triangle could have been accepted, so the traversal result is bit-identical (tests: culling on/off
+// agree on every ray; both agree with the oracle).  Rays with a zero/denormal/non-finite direction component
+// (`safe` false) are never culled.
 template <bool COUNT>
 SQT_HD void enter_step(const SceneView &sc, TravLane &L, Counters *cn) {
     const uint32_t count = L.meta & kCountMask;
