@@ -5,8 +5,11 @@
 // Haskell lists, so it is O(n log n) and handles the 1M / 10M triangle configs the list-based original
 // cannot reach.  Compile with -ffp-contract=off.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
+#include <thread>
 
 #include "squigly.hpp"
 
@@ -19,20 +22,52 @@ inline float hmax(float x, float y) { return x <= y ? y : x; }
 inline float hmin(float x, float y) { return x <= y ? x : y; }
 inline bool gt(float a, float b) { return !(a < b) && !(a == b); }     // compare == GT
 
+// A subtree under construction: nodes with indices local to the subtree, triangle order local to the subtree.
+struct Sub {
+    std::vector<BIHTreeNode> nodes;
+    std::vector<uint32_t> order;
+};
+
 class Builder {
   public:
     explicit Builder(BIH &out) : b_(out), tris_(out.triangles) {}
 
-    void run() {
+    // Large scenes: the top of the tree is split on this thread until there are a few subproblems per hardware
+    // thread; the subtrees are then built concurrently (they work on disjoint index ranges) and spliced into
+    // pre-order.  Every node is produced by the same arithmetic in the same order as the sequential build, so
+    // the tree is bit-identical (tests/test_host.py compares both against the oracle).
+    void run(unsigned threads) {
         const uint32_t n = (uint32_t)tris_.size();
         work_.resize(n); scratch_.resize(n);
         for (uint32_t i = 0; i < n; ++i) work_[i] = i;
-        b_.order.reserve(n);
         b_.bounds = boundingBox(0, n);
-        bih(b_.bounds, 0, n);
+        if (threads < 2 || n < (1u << 17)) {
+            Sub all;
+            all.order.reserve(n);
+            bih(all, b_.bounds, 0, n);
+            b_.tree = std::move(all.nodes); b_.order = std::move(all.order);
+            return;
+        }
+        grain_ = n / (4 * threads) + 1;
+        const int root = top(b_.bounds, 0, n);
+        std::vector<Sub> subs(tasks_.size());
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (size_t t = next.fetch_add(1); t < tasks_.size(); t = next.fetch_add(1))
+                bih(subs[t], tasks_[t].bbox, tasks_[t].lo, tasks_[t].hi);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < threads; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
+        b_.tree.clear(); b_.order.clear(); b_.order.reserve(n);
+        emit(root, subs);
     }
 
   private:
+    struct Task { Bounds bbox; uint32_t lo, hi; };
+    struct TopNode { int task = -1; BIHTreeNode node; int left = -1, right = -1; };
+
     // boundingBox = getBounds . concatMap vertices  (Geometry.hs:155-163,196-197): minimum/maximum per axis
     Bounds boundingBox(uint32_t lo, uint32_t hi) const {
         Bounds bb;
@@ -63,17 +98,9 @@ class Builder {
         s = s + proj(t.tFirst, ax); s = s + proj(t.tSecond, ax); s = s + proj(t.tThird, ax);
         return s / 3.0f;
     }
-    uint32_t leaf(uint32_t lo, uint32_t hi) {
-        BIHTreeNode n; n.leaf = true; n.first = (uint32_t)b_.order.size(); n.count = hi - lo;
-        b_.order.insert(b_.order.end(), work_.begin() + lo, work_.begin() + hi);
-        b_.tree.push_back(n);
-        return (uint32_t)b_.tree.size() - 1;
-    }
-    // bih (BIH.hs:67-80) over work_[lo, hi)
-    uint32_t bih(const Bounds &bbox, uint32_t lo, uint32_t hi) {
+    // split (BIH.hs:82-96) of work_[lo, hi): stable partition in place, returns the Branch node and the cut
+    BIHTreeNode split(const Bounds &bbox, uint32_t lo, uint32_t hi, uint32_t &mid) {
         const uint32_t n = hi - lo;
-        if (n < 15) return leaf(lo, hi);                                   // leafLimit = 15
-        // split (BIH.hs:82-96)
         const Axis ax = longestAxis(bbox);
         float acc = 0.0f;
         for (uint32_t i = lo; i < hi; ++i) acc = acc + centroid(work_[i], ax);
@@ -82,10 +109,10 @@ class Builder {
         uint32_t nl = 0, nr = 0;
         for (uint32_t i = lo; i < hi; ++i) {                               // filter underSplit / filter (not . underSplit)
             const uint32_t t = work_[i];
-            if (centroid(t, ax) < splitPlane) work_[lo + nl++] = t; else scratch_[nr++] = t;
+            if (centroid(t, ax) < splitPlane) work_[lo + nl++] = t; else scratch_[lo + nr++] = t;
         }
-        std::copy(scratch_.begin(), scratch_.begin() + nr, work_.begin() + lo + nl);
-        const uint32_t mid = lo + nl;
+        std::copy(scratch_.begin() + lo, scratch_.begin() + lo + nr, work_.begin() + lo + nl);
+        mid = lo + nl;
         float lbest = proj(bbox.lo, ax), rbest = proj(bbox.hi, ax);        // maximumDef leftSide / minimumDef rightSide
         bool any = false;
         for (uint32_t i = lo; i < mid; ++i) {
@@ -97,20 +124,85 @@ class Builder {
             const Triangle &t = tris_[work_[i]];
             for (const V3 *v : {&t.tFirst, &t.tSecond, &t.tThird}) { const float c = proj(*v, ax); rbest = any ? hmin(rbest, c) : c; any = true; }
         }
-        const uint32_t id = (uint32_t)b_.tree.size();
-        b_.tree.emplace_back();
-        b_.tree[id].leaf = false; b_.tree[id].axis = ax;
-        b_.tree[id].lmax = 0.001f + lbest;
-        b_.tree[id].rmin = (-0.001f) + rbest;
+        BIHTreeNode nd;
+        nd.leaf = false; nd.axis = ax;
+        nd.lmax = 0.001f + lbest;
+        nd.rmin = (-0.001f) + rbest;
+        return nd;
+    }
+    uint32_t leaf(Sub &out, uint32_t lo, uint32_t hi) {
+        BIHTreeNode n; n.leaf = true; n.first = (uint32_t)out.order.size(); n.count = hi - lo;
+        out.order.insert(out.order.end(), work_.begin() + lo, work_.begin() + hi);
+        out.nodes.push_back(n);
+        return (uint32_t)out.nodes.size() - 1;
+    }
+    // bih (BIH.hs:67-80) over work_[lo, hi), appended to `out` in pre-order
+    uint32_t bih(Sub &out, const Bounds &bbox, uint32_t lo, uint32_t hi) {
+        if (hi - lo < 15) return leaf(out, lo, hi);                        // leafLimit = 15
+        uint32_t mid;
+        const BIHTreeNode nd = split(bbox, lo, hi, mid);
+        const uint32_t id = (uint32_t)out.nodes.size();
+        out.nodes.push_back(nd);
         uint32_t l, r;
-        if (nl == 0 || nr == 0) {          // one side empty: both children become leaves, recursion stops (BIH.hs:70-75)
-            l = leaf(lo, mid); r = leaf(mid, hi);
+        if (mid == lo || mid == hi) {      // one side empty: both children become leaves, recursion stops (BIH.hs:70-75)
+            l = leaf(out, lo, mid); r = leaf(out, mid, hi);
         } else {
             const Bounds lb = boundingBox(lo, mid);
-            l = bih(lb, lo, mid);
+            l = bih(out, lb, lo, mid);
             const Bounds rb = boundingBox(mid, hi);
-            r = bih(rb, mid, hi);
+            r = bih(out, rb, mid, hi);
         }
+        out.nodes[id].left = l; out.nodes[id].right = r;
+        return id;
+    }
+    // the same recursion for the top of a large tree: ranges below the grain become tasks
+    int top(const Bounds &bbox, uint32_t lo, uint32_t hi) {
+        const int id = (int)top_.size();
+        top_.emplace_back();
+        if (hi - lo <= grain_) {
+            top_[id].task = (int)tasks_.size();
+            tasks_.push_back(Task{bbox, lo, hi});
+            return id;
+        }
+        uint32_t mid;
+        const BIHTreeNode nd = split(bbox, lo, hi, mid);
+        top_[id].node = nd;
+        int l, r;
+        if (mid == lo || mid == hi) {      // degenerate split: two leaves, handled as (tiny or huge) tasks that are leaves
+            l = (int)top_.size(); top_.emplace_back(); top_[l].task = -2; top_[l].node.first = lo; top_[l].node.count = mid - lo;
+            r = (int)top_.size(); top_.emplace_back(); top_[r].task = -2; top_[r].node.first = mid; top_[r].node.count = hi - mid;
+        } else {
+            const Bounds lb = boundingBox(lo, mid);
+            l = top(lb, lo, mid);
+            const Bounds rb = boundingBox(mid, hi);
+            r = top(rb, mid, hi);
+        }
+        top_[id].left = l; top_[id].right = r;
+        return id;
+    }
+    // pre-order emission of the top part with the finished subtrees spliced in
+    uint32_t emit(int t, const std::vector<Sub> &subs) {
+        const TopNode &tn = top_[t];
+        if (tn.task == -2) {               // forced leaf of a degenerate split
+            BIHTreeNode n; n.leaf = true; n.first = (uint32_t)b_.order.size(); n.count = tn.node.count;
+            b_.order.insert(b_.order.end(), work_.begin() + tn.node.first, work_.begin() + tn.node.first + tn.node.count);
+            b_.tree.push_back(n);
+            return (uint32_t)b_.tree.size() - 1;
+        }
+        if (tn.task >= 0) {
+            const Sub &s = subs[(size_t)tn.task];
+            const uint32_t node0 = (uint32_t)b_.tree.size(), tri0 = (uint32_t)b_.order.size();
+            for (BIHTreeNode n : s.nodes) {
+                if (n.leaf) n.first += tri0; else { n.left += node0; n.right += node0; }
+                b_.tree.push_back(n);
+            }
+            b_.order.insert(b_.order.end(), s.order.begin(), s.order.end());
+            return node0;
+        }
+        const uint32_t id = (uint32_t)b_.tree.size();
+        b_.tree.push_back(tn.node);
+        const uint32_t l = emit(tn.left, subs);
+        const uint32_t r = emit(tn.right, subs);
         b_.tree[id].left = l; b_.tree[id].right = r;
         return id;
     }
@@ -118,6 +210,9 @@ class Builder {
     BIH &b_;
     const std::vector<Triangle> &tris_;
     std::vector<uint32_t> work_, scratch_;
+    std::vector<TopNode> top_;
+    std::vector<Task> tasks_;
+    uint32_t grain_ = 0;
 };
 
 }  // namespace
@@ -126,7 +221,9 @@ BIH makeBIH(ParsedScene scene) {
     BIH b;
     b.triangles = std::move(scene.triangles);
     b.materials = std::move(scene.materials);
-    Builder(b).run();
+    unsigned threads = std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("SQT_BIH_THREADS")) threads = (unsigned)std::atoi(e);
+    Builder(b).run(threads ? threads : 1);
     return b;
 }
 

@@ -57,6 +57,23 @@ def test_bih_builder_matches_oracle_on_synthetic_scenes(gen, n):
     assert np.array_equal(hs.tris["orig_index"], leaf.astype(np.uint32))
 
 
+def test_parallel_bih_build_is_bit_identical(monkeypatch):
+    """Above 2^17 triangles the host builder splits the top of the tree on one thread and builds the subtrees
+    concurrently; the spliced tree must equal the sequential build and the oracle's literal build bit for bit."""
+    v9, mi, mats = scenes.triangle_soup(150_000, seed=11)
+    v9 = v9 * np.float32(8.0)
+    monkeypatch.setenv("SQT_BIH_THREADS", "6")
+    par = pysqt.HostScene.from_arrays(v9, mi, mats)
+    monkeypatch.setenv("SQT_BIH_THREADS", "1")
+    seq = pysqt.HostScene.from_arrays(v9, mi, mats)
+    osc = O.Scene.from_arrays(v9, mi, mats)
+    osc.make_bih()
+    root, nodes, leaf = osc.export_bih()
+    for hs in (par, seq):
+        assert np.array_equal(hs.root, root) and np.array_equal(flat_nodes_as_u32(hs), nodes)
+        assert np.array_equal(hs.tris["orig_index"], leaf.astype(np.uint32))
+
+
 def test_degenerate_builds():
     mats = np.array([[0, .5, .5, .5, 0, 0, 0, 0]], np.float32)
     # fewer than leafLimit triangles: a single Leaf (BIH.hs:69)
