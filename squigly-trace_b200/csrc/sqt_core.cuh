@@ -405,7 +405,6 @@ SQT_HD void tri_step(const SceneView &sc, TravLane &L, Counters *cn) {
     const TriData d = tri_load(sc, L.child + (uint32_t)L.i);
     tri_apply<COUNT>(L, d, cn);
 }
-
 // A subtree returned `cur`: pop entries until one of them sends the lane into a far subtree (-> ST_DESC) or
 // the stack is empty (-> ST_DONE).  Pops that only merge or propagate are a handful of instructions each.
 SQT_HD void ret_step(const SceneView &sc, TravLane &L) {
