@@ -50,6 +50,23 @@ def test_primary_rays_bit_exact(gpu_ctx, host_scene, oracle_scene, camera):
     assert st["rays_traced"] == len(org)
 
 
+def test_gpu_matches_committed_golden_fixtures(gpu_ctx, host_scene, camera):
+    """tests/golden/scene_obj_golden.json (made by tests/golden/make_golden.py with the oracle): the device must
+    reproduce the hashed hit indices / dist / points of the 540x540 reference-default frame and the hashed render."""
+    import json, os
+    from golden.make_golden import sha
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "scene_obj_golden.json")))
+    gpu_ctx.upload(host_scene)
+    org, dirs = O.make_rays(O.make_params(540, 540, 1), camera)
+    tri, dist, point = gpu_ctx.intersect_batch(org, dirs)
+    g = gold["primary_540"]
+    assert int((tri >= 0).sum()) == g["hits"]
+    assert sha(tri) == g["sha_tri"] and sha(dist) == g["sha_dist"] and sha(point) == g["sha_point"]
+    out = gpu_ctx.render(camera, pysqt.make_params(64, 64, 4, max_depth=3, seed=1))
+    g = gold["render_64x64_4spp_d3_seed1_sqttrig"]
+    assert sha(out["accum"]) == g["sha_accum"] and sha(out["rgb8"]) == g["sha_rgb8"]
+
+
 def test_literal_nonsquare_primary_rays(gpu_ctx, host_scene, oracle_scene, camera):
     gpu_ctx.upload(host_scene)
     org, dirs = O.make_rays(O.make_params(320, 200, 1, literal=True), camera)
@@ -269,6 +286,30 @@ def test_every_path_kernel_scheduler_is_bit_exact(host_scene, oracle_scene, came
         if flags:
             assert out["stats"]["rays_traced"] == ref["rays"]
     ctx.close()
+
+
+def test_baseline_config2_at_full_size(gpu_ctx, host_scene, oracle_scene, camera):
+    """BASELINE.json configs[1] exactly: data/scene.obj, 1920x1080, 1024 spp, 8 bounces (2.1e9 samples, 5.3e9 rays).
+    Size-independent checks: exact sample accounting; misses are exactly black; twelve pixels re-rendered by the
+    oracle with all their 1024 samples match bit for bit (so the 16 accumulation rounds add in sample order); the
+    RGB8 frame equals the oracle's tone map of the device's sums."""
+    gpu_ctx.upload(host_scene)
+    W, H, spp, depth = 1920, 1080, 1024, 8
+    p = pysqt.make_params(W, H, spp, max_depth=depth, seed=0)
+    out = gpu_ctx.render(camera, p)
+    acc, st = out["accum"], out["stats"]
+    assert st["samples"] == W * H * spp
+    assert 5.0e9 < st["rays_traced"] < 5.6e9
+    org, dirs = O.make_rays(O.make_params(W, H, 1), camera)
+    miss = (gpu_ctx.intersect_batch(org, dirs)[0] < 0).reshape(H, W)
+    assert np.all(acc[miss] == 0) and np.all(acc[~miss].sum(-1) >= 0)
+    op = O.make_params(W, H, spp, max_depth=depth, seed=0, trig=1)
+    rng = np.random.default_rng(5)
+    hit_pixels = np.flatnonzero(~miss.ravel())
+    for pix in rng.choice(hit_pixels, 12, replace=False):
+        want = O.render_window(oracle_scene, camera, op, int(pix), int(pix) + 1)
+        assert np.array_equal(bits(acc.reshape(-1, 3)[pix]), bits(want[0])), "pixel %d" % pix
+    assert np.array_equal(out["rgb8"], O.tone_map(acc, spp, trig=1))
 
 
 def test_schedulers_and_culling_agree_at_full_size(host_scene, camera, monkeypatch):
