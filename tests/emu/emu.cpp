@@ -173,12 +173,14 @@ long long emu_trace_lane(emu_scene *s, const sqt_camera *cam, const sqt_render_p
     L.stack = stack; L.state = ST_DONE; L.sp = 0; L.cur.tri = -1;
     long long n = 0;
     for (;;) {
-        if (L.state == ST_DONE) { pol.regen<false>(s->view, L, &cn); if (n < cap) out[n] = 'R'; n++; }
+        if (L.state == ST_DONE) { pol.regen<false>(s->view, L, &cn); if (n < cap) out[n] = 'R';
+            n++; }
         if (L.state == ST_EXIT) break;
         if (L.state == ST_RET || L.state == ST_DESC) {
             if (L.state == ST_RET) ret_step(s->view, L);
             if (L.state == ST_DESC) desc_step<false>(s->view, L, &cn);
-            if (n < cap) out[n] = 'T'; n++;
+            if (n < cap) out[n] = 'T';
+            n++;
         } else if (L.state == ST_ENTER) { enter_step<false>(s->view, L, &cn); if (n < cap) out[n] = 'E'; n++; }
         else if (L.state == ST_LEAF) { tri_step<false>(s->view, L, &cn); if (n < cap) out[n] = 'L'; n++; }
     }
