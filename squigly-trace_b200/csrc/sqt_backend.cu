@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, Rou
 
 // ------------------------------------------------------------------------------ ray pools
 // k_paths_pool: the same per-ray logic as k_paths, scheduled differently.  Every warp owns a POOL of P = 32*K rays
-// whose state lives in shared memory (structure of arrays, 24 words per ray; traversal stacks and per-path material
-// lists in global memory, one region per pool slot).  Each round the warp counts how many of its rays wait for a
+// whose state lives in shared memory (structure of arrays, 16 words per ray; traversal stacks, per-path material
+// lists and the integrator state of a slot in global memory, one region per pool slot).  Each round the warp counts how many of its rays wait for a
 // traversal step, a leaf entry, a triangle test or regeneration, picks the kind with the most waiting rays, gathers
 // up to 32 of them onto its lanes (rank by ballot, scatter slot ids through shared memory), runs a short burst of
 // that one kind of step with (nearly) all lanes active, and writes the rays back.  With one ray per lane at most
@@ -199,10 +199,13 @@ __global__ void __launch_bounds__(128) k_paths(SceneView sc, RenderParams p, Rou
 #ifndef SQT_POOL_MIN_BLOCKS
 #define SQT_POOL_MIN_BLOCKS 8
 #endif
-struct PoolTune { int burst_t, burst_l, c_min, merge_enter; };   // merge_enter: leaf entry runs inside the traversal burst
+struct PoolTune { int burst_t, burst_l, c_min; };
 
-enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_META, PF_I, PF_CTRI, PF_CT, PF_CDIST,
-       PF_SP, PF_FLAGS, PF_DFAC, PF_WORDS };      // 18 words = 72 B per ray in shared memory
+// 16 words = 64 B per ray in shared memory.  PF_MI holds `meta` while the ray descends / enters and `i` while it is in a
+// leaf; PF_FLAGS = state | safe << 8 | sgn << 16 | sp << 24.  (4 warps x 64 rays x 64 B + lists = 16.5 KB per CTA, so
+// 8 CTAs fit the 132 KB shared-memory carve-out and ~90 KB stay L1.)
+enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_MI, PF_CTRI, PF_CT, PF_CDIST, PF_FLAGS,
+       PF_DFAC, PF_WORDS };
 // the integrator state of a slot (PathRay) is only touched by regeneration: 8 words per slot in global memory
 
 template <bool COUNT, int K>
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
     for (int k = 0; k < K; ++k) {
         const int slot = lane + 32 * k;
         PW(PF_FLAGS, slot) = (uint32_t)ST_DONE;
-        PW(PF_SP, slot) = 0u; PW(PF_CTRI, slot) = 0xffffffffu;
+        PW(PF_CTRI, slot) = 0xffffffffu;
         gpath[2 * (gslot0 + slot)] = make_uint4(0u, 0u, 0u, 0u);
         gpath[2 * (gslot0 + slot) + 1] = make_uint4(0u, 0u, 0u, 0u);      // saved_j = -1 (stored +1), any_emit = in_flight = false
     }
@@ -237,8 +240,8 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             sk[k] = (int)(PW(PF_FLAGS, lane + 32 * k) & 0xffu);
-            n_t += __popc(__ballot_sync(FULL, sk[k] == ST_DESC || sk[k] == ST_RET || (tn.merge_enter && sk[k] == ST_ENTER)));
-            n_e += __popc(__ballot_sync(FULL, !tn.merge_enter && sk[k] == ST_ENTER));
+            n_t += __popc(__ballot_sync(FULL, sk[k] == ST_DESC || sk[k] == ST_RET));
+            n_e += __popc(__ballot_sync(FULL, sk[k] == ST_ENTER));
             n_l += __popc(__ballot_sync(FULL, sk[k] == ST_LEAF));
             n_r += __popc(__ballot_sync(FULL, sk[k] == ST_DONE));
         }
@@ -255,8 +258,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const bool mine = kind == 0 ? sk[k] == ST_LEAF
-                            : (kind == 1 ? (sk[k] == ST_DESC || sk[k] == ST_RET || (tn.merge_enter && sk[k] == ST_ENTER))
-                                         : (kind == 2 ? sk[k] == ST_ENTER : sk[k] == ST_DONE));
+                            : (kind == 1 ? (sk[k] == ST_DESC || sk[k] == ST_RET) : (kind == 2 ? sk[k] == ST_ENTER : sk[k] == ST_DONE));
             const unsigned b = __ballot_sync(FULL, mine);
             const int rank = base + __popc(b & lt_mask);
             if (mine && rank < 32) sel[rank] = (uint32_t)(lane + 32 * k);
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             if (act) {
                 L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
                 L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
-                L.child = PW(PF_CHILD, slot); L.i = (int)PW(PF_I, slot);
+                L.child = PW(PF_CHILD, slot); L.i = (int)PW(PF_MI, slot);
                 L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
                 L.state = ST_LEAF;
             } else L.state = ST_EXIT;
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 if (!__any_sync(FULL, L.state == ST_LEAF)) break;
             }
             if (act) {
-                PW(PF_I, slot) = (uint32_t)L.i;
+                PW(PF_MI, slot) = (uint32_t)L.i;
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
                 if (L.state != ST_LEAF) PW(PF_FLAGS, slot) = (PW(PF_FLAGS, slot) & ~0xffu) | (uint32_t)L.state;
             }
@@ -293,23 +295,20 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
                 L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
                 L.dfx = u2f(PW(PF_DFX, slot)); L.dfy = u2f(PW(PF_DFY, slot)); L.dfz = u2f(PW(PF_DFZ, slot));
-                L.child = PW(PF_CHILD, slot); L.meta = PW(PF_META, slot); L.sp = (int)PW(PF_SP, slot);
+                L.child = PW(PF_CHILD, slot); L.meta = PW(PF_MI, slot);
                 L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
-                L.dfac = u2f(PW(PF_DFAC, slot)); L.i = (int)PW(PF_I, slot);
                 fl = PW(PF_FLAGS, slot);
-                L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u;
+                L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
             } else L.state = ST_EXIT;
             for (int b = 0; b < tn.burst_t; ++b) {
                 if (L.state == ST_RET) ret_step(sc, L);
                 if (L.state == ST_DESC) desc_step<COUNT>(sc, L, &cn);
-                if (tn.merge_enter && L.state == ST_ENTER) enter_step<COUNT>(sc, L, &cn);     // culled lanes fall back to ST_RET
                 if (!__any_sync(FULL, L.state == ST_DESC || L.state == ST_RET)) break;
             }
             if (act) {
-                PW(PF_I, slot) = (uint32_t)L.i;
-                PW(PF_CHILD, slot) = L.child; PW(PF_META, slot) = L.meta; PW(PF_SP, slot) = (uint32_t)L.sp;
+                PW(PF_CHILD, slot) = L.child; PW(PF_MI, slot) = L.meta;
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
-                PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)L.state;
+                PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
             }
         } else if (kind == 2) {
             // ---- leaf entry: record fetch + conservative culling
@@ -317,13 +316,13 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
                 L.dfx = u2f(PW(PF_DFX, slot)); L.dfy = u2f(PW(PF_DFY, slot)); L.dfz = u2f(PW(PF_DFZ, slot));
                 L.dfac = u2f(PW(PF_DFAC, slot));
-                L.child = PW(PF_CHILD, slot); L.meta = PW(PF_META, slot);
+                L.child = PW(PF_CHILD, slot); L.meta = PW(PF_MI, slot);
                 const uint32_t fl = PW(PF_FLAGS, slot);
                 L.safe = ((fl >> 8) & 1u) != 0u;
                 L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f; L.i = 0;
                 L.state = ST_ENTER;
                 enter_step<COUNT>(sc, L, &cn);
-                PW(PF_CHILD, slot) = L.child; PW(PF_I, slot) = (uint32_t)L.i; PW(PF_CTRI, slot) = (uint32_t)L.cur.tri;
+                PW(PF_CHILD, slot) = L.child; PW(PF_MI, slot) = (uint32_t)L.i; PW(PF_CTRI, slot) = (uint32_t)L.cur.tri;
                 PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)L.state;
             }
         } else {
@@ -346,10 +345,10 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 PW(PF_OX, slot) = f2u(L.r.ox); PW(PF_OY, slot) = f2u(L.r.oy); PW(PF_OZ, slot) = f2u(L.r.oz);
                 PW(PF_DX, slot) = f2u(L.r.dx); PW(PF_DY, slot) = f2u(L.r.dy); PW(PF_DZ, slot) = f2u(L.r.dz);
                 PW(PF_DFX, slot) = f2u(L.dfx); PW(PF_DFY, slot) = f2u(L.dfy); PW(PF_DFZ, slot) = f2u(L.dfz);
-                PW(PF_CHILD, slot) = L.child; PW(PF_META, slot) = L.meta; PW(PF_I, slot) = (uint32_t)L.i;
+                PW(PF_CHILD, slot) = L.child; PW(PF_MI, slot) = L.state == ST_LEAF ? (uint32_t)L.i : L.meta;
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
-                PW(PF_SP, slot) = (uint32_t)L.sp; PW(PF_DFAC, slot) = f2u(L.dfac);
-                PW(PF_FLAGS, slot) = (uint32_t)L.state | (L.safe ? 0x100u : 0u) | (L.sgn << 16);
+                PW(PF_DFAC, slot) = f2u(L.dfac);
+                PW(PF_FLAGS, slot) = (uint32_t)L.state | (L.safe ? 0x100u : 0u) | (L.sgn << 16) | ((uint32_t)L.sp << 24);
                 gp[0] = make_uint4(q.sidx, (uint32_t)q.j, (uint32_t)q.stream, (uint32_t)(q.stream >> 32));
                 gp[1] = make_uint4(f2u(q.saved_r), (uint32_t)(q.saved_j + 1) | (q.any_emit ? 0x10000u : 0u) | (q.in_flight ? 0x20000u : 0u), 0u, 0u);
             }
@@ -485,7 +484,7 @@ struct sqt_ctx {
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
     Tune tune = {8, 1, 8};
     int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
-    PoolTune pool_tune = {4, 8, 16, 0};
+    PoolTune pool_tune = {4, 8, 16};
     int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1
     uint32_t *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0;
     // group
@@ -533,8 +532,8 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
     if (const char *t = getenv("SQT_POOL")) { int k = atoi(t); if (k >= 0 && k <= 4) c->pool_k = k; }
     if (const char *t = getenv("SQT_POOL_BLOCKS")) c->pool_blocks = atoi(t);
     if (const char *t = getenv("SQT_POOL_TUNE")) {
-        int a, b, cm, me = 0;
-        if (sscanf(t, "%d,%d,%d,%d", &a, &b, &cm, &me) >= 3) c->pool_tune = {a, b, cm, me};
+        int a, b, cm;
+        if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->pool_tune = {a, b, cm};
     }
     if (const char *t = getenv("SQT_SBUF_MB")) { long long mb = atoll(t); if (mb > 0) c->sbuf_budget = mb << 20; }
     if (const char *t = getenv("SQT_TUNE")) {        // "a_leave,b_leave,c_min" -- scheduling knobs only, results do not depend on them
