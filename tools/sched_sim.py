@@ -189,3 +189,48 @@ if __name__ == "__main__":
                               (64, 4, 2, 120), (96, 6, 2, 120), (128, 14, 4, 120)]:
         c, r, u = simulate_pool(tr128, slots, bl, bt, ov)
         print("pool slots=%3d burst L=%d T=%d overhead=%3d : %6.0f slots/ray  lane util %.2f" % (slots, bl, bt, ov, c / r, u))
+
+
+def simulate_pool_refill(tr_all, slots=64, burst=8, overhead=86, refill_cost=30, c_min=16):
+    """Pool with LANE-LEVEL REFILL: inside a burst a lane whose ray leaves the step kind writes it back and takes the next
+    waiting ray of that kind (charged `refill_cost` instruction slots per iteration in which any lane refills)."""
+    tr = tr_all[:slots]
+    pos = [0] * len(tr)
+    cost = 0
+    rays = sum(t.count("R") for t in tr)
+
+    def state(i):
+        return tr[i][pos[i]] if pos[i] < len(tr[i]) else "X"
+    num = den = 0
+    while True:
+        groups = {"R": [], "T": [], "E": [], "L": []}
+        for i in range(len(tr)):
+            s = state(i)
+            if s != "X": groups[s].append(i)
+        if not any(groups.values()): break
+        cand = {k: len(v) for k, v in groups.items()}
+        if cand["R"] < c_min and (cand["T"] or cand["E"] or cand["L"]): cand["R"] = 0
+        kind = max(cand, key=lambda k: cand[k])
+        waiting = list(groups[kind])
+        lanes = [waiting.pop(0) for _ in range(min(32, len(waiting)))]
+        cost += overhead
+        for b in range(burst if kind in "TL" else 1):
+            refilled = False
+            for li, ray in enumerate(lanes):
+                if ray is not None and state(ray) != kind:
+                    lanes[li] = waiting.pop(0) if waiting else None
+                    refilled = refilled or lanes[li] is not None
+            act = [r for r in lanes if r is not None and state(r) == kind]
+            if not act: break
+            for r in act: pos[r] += 1
+            cost += COST[kind] + 4 + (refill_cost if refilled else 0)
+            num += len(act); den += 32
+    return cost, rays, num / max(den, 1)
+
+
+if __name__ == "__main__":
+    tr256 = traces(n_lanes=256, pixels_per_lane=1, spp=6)
+    for slots in (64, 96, 128, 256):
+        for burst in (4, 8, 16):
+            c, r, u = simulate_pool_refill(tr256, slots, burst)
+            print("pool+refill slots=%3d burst=%2d : %6.0f slots/ray  lane util %.2f" % (slots, burst, c / r, u))
