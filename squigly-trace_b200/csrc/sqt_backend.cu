@@ -22,6 +22,7 @@
 #include <string.h>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/sqt.h"
@@ -66,8 +67,69 @@ __device__ __forceinline__ void flush_stats(DeviceStats *ds, const PathStats &st
 // change the order in which lanes get served, never a result):
 //   a_leave : leave the traversal phase once at most this many lanes still want a traversal step
 //   b_leave : leave the triangle phase once fewer than this many lanes still have triangles to test
+//             (0 = the warp-cooperative triangle phase below, which always runs to completion)
 //   c_min   : run the regeneration phase only when at least this many lanes are done (or nothing else can run)
 struct Tune { int a_leave, b_leave, c_min; };
+
+// Warp-cooperative triangle phase.  The lanes that wait in a leaf hold (first triangle, triangles left); their
+// remaining (ray, triangle) tests are laid out consecutively by an exclusive scan and executed 32 at a time, one
+// test per lane, whichever lane owns the ray: the owner of test p is found by a binary search over the scan
+// (shuffles), the ray comes from the owner by shuffle.  Accepted hits (about one test in seventy) are handed back
+// to the owner one after the other in test order, i.e. from the leaf's last triangle to its first, so every ray
+// sees exactly the sequence of min' applications of BIH.hs:105-109 (base-4.9 minimumBy = foldr1 min').
+// Moller-Trumbore is a pure function of (ray, triangle), so only the lane that evaluates it changes.
+template <bool COUNT>
+__device__ __forceinline__ void leaf_pairs(const SceneView &sc, TravLane &L, Counters *cn) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool in_leaf = L.state == ST_LEAF;
+    const int left = in_leaf ? L.i + 1 : 0;
+    const int cnt = left < 1024 ? left : 1024;            // a pathological leaf is worked off over several phases
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int start = incl - cnt;
+    const int total = __shfl_sync(FULL, incl, 31);
+    for (int base = 0; base < total; base += 32) {
+        const int pr = base + lane;
+        int own = 0;                                       // first lane whose inclusive scan exceeds pr
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const int v = __shfl_sync(FULL, incl, own + s - 1);
+            if (v <= pr) own += s;
+        }
+        Ray r;
+        r.ox = __shfl_sync(FULL, L.r.ox, own); r.oy = __shfl_sync(FULL, L.r.oy, own); r.oz = __shfl_sync(FULL, L.r.oz, own);
+        r.dx = __shfl_sync(FULL, L.r.dx, own); r.dy = __shfl_sync(FULL, L.r.dy, own); r.dz = __shfl_sync(FULL, L.r.dz, own);
+        const uint32_t first = __shfl_sync(FULL, L.child, own);
+        const int oi = __shfl_sync(FULL, L.i, own), os = __shfl_sync(FULL, start, own);
+        const uint32_t idx = first + (uint32_t)(oi - (pr - os));
+        bool hit = false;
+        float t = 0.0f, dist = 0.0f;
+        if (pr < total) {
+            const TriData d = tri_load(sc, idx);
+            int stage;
+            hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
+            if (COUNT) { cn->mt_pass_a += stage >= 1; cn->mt_pass_u += stage >= 2; cn->mt_pass_v += stage >= 3; cn->mt_accept += stage >= 4; }
+        }
+        unsigned hm = __ballot_sync(FULL, hit);
+        while (hm != 0u) {                                 // rare: hand each accepted hit to its owner, in test order
+            const int src = __ffs(hm) - 1;
+            hm &= hm - 1u;
+            const int o_s = __shfl_sync(FULL, own, src);
+            const float t_s = __shfl_sync(FULL, t, src), d_s = __shfl_sync(FULL, dist, src);
+            const uint32_t i_s = __shfl_sync(FULL, idx, src);
+            if (lane == o_s && (L.cur.tri < 0 || !cmp_gt(d_s, L.cur.dist))) { L.cur.tri = (int)i_s; L.cur.t = t_s; L.cur.dist = d_s; }
+        }
+    }
+    if (in_leaf) {
+        L.i -= cnt;
+        if (L.i < 0) L.state = ST_RET;
+    }
+}
 
 // The persistent warp loop.  Every lane of the warp stays in it until all 32 have run out of work.  A round is
 // three phases, each a tight loop whose trip count is decided by a warp vote: regeneration (consume the finished
@@ -75,6 +137,9 @@ struct Tune { int a_leave, b_leave, c_min; };
 // Moller-Trumbore test).  The votes force the 32 lanes back together at every phase boundary; an ordinary
 // per-lane loop nest compiles to code where the lanes drift apart through the data-dependent traversal and
 // never reconverge (measured: 2.4 of 32 lanes active, profiles/r01_k_paths_v0_divergent.txt).
+template <class P, class = void> struct has_warp_regen : std::false_type {};
+template <class P> struct has_warp_regen<P, std::void_t<decltype(P::kWarpRegen)>> : std::true_type {};
+
 template <bool COUNT, class Policy>
 __device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Counters *cn, const Tune tn) {
     const unsigned FULL = 0xffffffffu;
@@ -90,7 +155,8 @@ __device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Coun
         const unsigned m_done = __ballot_sync(FULL, L.state == ST_DONE);
         const unsigned m_busy = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET || L.state == ST_LEAF || L.state == ST_ENTER);
         if (m_done != 0u && (__popc(m_done) >= tn.c_min || m_busy == 0u)) {
-            if (L.state == ST_DONE) pol.template regen<COUNT>(sc, L, cn);
+            if constexpr (has_warp_regen<Policy>::value) pol.template regen_warp<COUNT>(sc, L, cn, L.state == ST_DONE);
+            else { if (L.state == ST_DONE) pol.template regen<COUNT>(sc, L, cn); }
             __syncwarp(FULL);
         } else if (m_busy == 0u) break;                       // every lane is ST_EXIT
         // ---- traversal steps (stack pops + one branch visit) while more than a_leave lanes want one; then every
@@ -114,8 +180,12 @@ __device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Coun
             }
             break;
         }
-        // ---- triangle steps
+        // ---- triangle tests: all lanes share the tests of the lanes that wait in a leaf, or one test per lane and step
         unsigned m = __ballot_sync(FULL, L.state == ST_LEAF);
+        if (tn.b_leave == 0) {
+            if (m != 0u) leaf_pairs<COUNT>(sc, L, cn);
+            continue;
+        }
         while (m != 0u) {
             if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, cn);
             m = __ballot_sync(FULL, L.state == ST_LEAF);
@@ -326,22 +396,29 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)L.state;
             }
         } else {
-            // ---- regeneration: consume the finished hit, shade, start the next ray (or the next sample)
+            // ---- regeneration: consume the finished hit, shade, start the next ray (or the next sample); staged, all
+            //      gathered lanes together (path_regen_warp)
+            PathRay q;
+            path_ray_init(q);
+            uint4 *gp = gpath + 2 * (gslot0 + slot);
+            L.dfx = L.dfy = L.dfz = 0.0f; L.dfac = 0.0f; L.child = 0u; L.meta = 0u; L.i = 0; L.sp = 0; L.safe = true; L.sgn = 0u;
+            L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
+            L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
+            L.state = ST_EXIT;
             if (act) {
                 L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
                 L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
                 L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
-                L.dfx = L.dfy = L.dfz = 0.0f; L.dfac = 0.0f; L.child = 0u; L.meta = 0u; L.i = 0; L.sp = 0; L.safe = true; L.sgn = 0u;
                 L.state = ST_DONE;
-                PathRay q;
-                uint4 *gp = gpath + 2 * (gslot0 + slot);
                 const uint4 g0 = gp[0], g1 = gp[1];
                 const uint32_t pf = g1.y;
                 q.sidx = g0.x; q.j = (int)g0.y;
                 q.stream = (unsigned long long)g0.z | ((unsigned long long)g0.w << 32);
                 q.saved_r = u2f(g1.x); q.saved_j = (int)(pf & 0xffffu) - 1;
                 q.any_emit = ((pf >> 16) & 1u) != 0u; q.in_flight = ((pf >> 17) & 1u) != 0u;
-                path_regen<COUNT>(sc, p, rd, fetch, st, q, gpm + (size_t)(gslot0 + slot) * SQT_MAX_DEPTH, L, &cn);
+            }
+            path_regen_warp<COUNT>(sc, p, rd, fetch, st, q, gpm + (size_t)(gslot0 + slot) * SQT_MAX_DEPTH, L, &cn, act);
+            if (act) {
                 PW(PF_OX, slot) = f2u(L.r.ox); PW(PF_OY, slot) = f2u(L.r.oy); PW(PF_OZ, slot) = f2u(L.r.oz);
                 PW(PF_DX, slot) = f2u(L.r.dx); PW(PF_DY, slot) = f2u(L.r.dy); PW(PF_DZ, slot) = f2u(L.r.dz);
                 PW(PF_DFX, slot) = f2u(L.dfx); PW(PF_DFY, slot) = f2u(L.dfy); PW(PF_DFZ, slot) = f2u(L.dfz);
@@ -482,7 +559,7 @@ struct sqt_ctx {
     int *d_tri = nullptr;
     // pinned host staging for image I/O
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
-    Tune tune = {8, 1, 8};
+    Tune tune = {8, 0, 8};
     int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
     PoolTune pool_tune = {4, 8, 16};
     int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1

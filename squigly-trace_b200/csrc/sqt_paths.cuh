@@ -96,78 +96,139 @@ SQT_HD float path_draw(const RenderParams &p, PathRay &q, uint32_t jj) {
     return random_r01(k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3])));
 }
 
+// ---- the stages of path regeneration.  path_regen strings them together for one lane; path_regen_warp (device only)
+//      runs every stage for all regenerating lanes of a warp at once, so that the expensive stages (bounce, start_ray)
+//      execute once with many lanes instead of once per control-flow path with a few.
+struct RegenLane {
+    int htri; float ht;          // the hit to shade (htri < 0: none)
+    float refl;                  // `reflective` of the shaded material (Lib.hs:157)
+};
+
+// A: the ray of Lib.hs:131 came back.  Returns true when the path is over (no hit).
+SQT_HD bool path_consume(PathRay &q, PathStats &st, const TravLane &L, RegenLane &g) {
+    g.htri = -1; g.ht = 0.0f; g.refl = 0.0f;
+    if (!q.in_flight) return false;
+    q.in_flight = false;
+    st.rays += 1;
+    if (L.cur.tri >= 0) { g.htri = L.cur.tri; g.ht = L.cur.t; q.j += 1; return false; }
+    return true;
+}
+// B1: the sample is finished: store its radiance (samples that never met an emitter are exactly +0, which the
+//     zero-filled buffer already holds)
+SQT_HD void path_finish(const SceneView &sc, const RoundInfo &rd, const uint16_t *pm, const PathRay &q, PathStats &st, RegenLane &g) {
+    if (q.any_emit) {
+        float lr, lg, lb;
+        fold_path(sc, pm, q.j, lr, lg, lb);
+        rd.sbuf[3 * (size_t)q.sidx] = lr; rd.sbuf[3 * (size_t)q.sidx + 1] = lg; rd.sbuf[3 * (size_t)q.sidx + 2] = lb;
+    }
+    st.samples += 1;
+    g.htri = -1;
+}
+// B2: next sample.  0 = the queue is empty, 1 = item skipped (padding / beyond the sample range) -- fetch again,
+//     2 = the primary hit is known (shade it), 3 = the primary ray has to be traced (primary reuse off)
+enum : int { NS_EMPTY = 0, NS_SKIP = 1, NS_SHADE = 2, NS_TRACE = 3 };
+template <class Fetch>
+SQT_HD int path_next_sample(const RenderParams &p, const RoundInfo &rd, Fetch &fetch, PathStats &st, PathRay &q, TravLane &L, RegenLane &g) {
+    const long long w = fetch();
+    if (w < 0) return NS_EMPTY;
+    const long long slot = w >> rd.log2_s;
+    const int ks = (int)(w & ((1ll << rd.log2_s) - 1));
+    const int k = rd.k0 + ks;
+    if (k >= rd.k1) return NS_SKIP;
+    const long long pixel = rd.pixel_list ? (long long)rd.pixel_list[slot] : work_to_pixel(p, slot);
+    if (pixel < 0) return NS_SKIP;
+    const int py = (int)(pixel / p.cols), px = (int)(pixel % p.cols);
+    q.stream = (unsigned long long)p.spp * ((unsigned long long)px + (unsigned long long)py * (unsigned long long)p.seed_stride)
+               + (unsigned long long)k;
+    q.sidx = (uint32_t)((long long)ks * rd.slot_stride + slot);
+    q.any_emit = false; q.saved_j = -1;
+    L.r = make_ray(p, py, px);
+    if (rd.prim) {
+        // the primary ray is the same for every sample of a pixel (Lib.hs:81): its hit was traced once
+        const int2 ph = rd.prim[pixel];
+        g.htri = ph.x; g.ht = u2f((uint32_t)ph.y); q.j = 0;
+        st.primary_reused += 1;
+        return NS_SHADE;
+    }
+    q.j = -1; q.in_flight = true;                     // primary reuse off: trace it again like Lib.hs:84 does
+    return NS_TRACE;
+}
+// C: shade the hit of bounce j (raytrace, Lib.hs:127-137).  Returns true when the path goes on with a bounce.
+SQT_HD bool path_shade(const SceneView &sc, const RenderParams &p, uint16_t *pm, PathRay &q, RegenLane &g) {
+    const uint32_t mat = surface_material(sc, g.htri);
+    pm[q.j] = (uint16_t)mat;
+    const float4 *mp = sc.mats + 3 * (size_t)mat;
+    const float4 m0 = SQT_LDG4(mp);
+    const uint32_t mflags = f2u(SQT_LDG4(mp + 2).w);
+    q.any_emit = q.any_emit || (mflags & kMatEmits);
+    g.refl = m0.x;
+    return !((q.j + 1 > p.max_depth - 1) || (p.terminate_on_black && (mflags & kMatBlack)));
+}
+// D: bounceRay (Lib.hs:155-160); L.r is the ray that produced the hit and becomes the bounced ray
+SQT_HD void path_bounce(const SceneView &sc, const RenderParams &p, PathRay &q, TravLane &L, const RegenLane &g) {
+    const float x = path_draw(p, q, (uint32_t)q.j);
+    float v = 0.0f;
+    const bool scatter = g.refl < x;
+    if (scatter) { v = path_draw(p, q, (uint32_t)q.j + 1u); q.saved_r = v; q.saved_j = q.j + 1; } else q.saved_j = -1;
+    L.r = bounce_ray(sc, L.r, g.htri, g.ht, scatter, x, v);
+    q.in_flight = true;
+}
+
 // called when L.state == ST_DONE: consume the hit (if a ray was in flight), then shade / start the next sample until
 // the slot has a ray to trace (-> start_ray) or the queue is empty (-> ST_EXIT).  pm: SQT_MAX_DEPTH entries of
 // ray-private memory holding the material of every shaded bounce of the current path.
 template <bool COUNT, class Fetch>
 SQT_HD void path_regen(const SceneView &sc, const RenderParams &p, const RoundInfo &rd, Fetch &fetch, PathStats &st, PathRay &q,
                        uint16_t *pm, TravLane &L, Counters *cn) {
-    bool path_over = false;
-    int htri = -1; float ht = 0.0f;
-    if (q.in_flight) {                                    // the ray of Lib.hs:131 came back
-        q.in_flight = false;
-        st.rays += 1;
-        if (L.cur.tri >= 0) { htri = L.cur.tri; ht = L.cur.t; q.j += 1; }
-        else path_over = true;
-    }
+    RegenLane g;
+    bool path_over = path_consume(q, st, L, g);
     for (;;) {
-        if (path_over) {
-            // ---- the sample is finished: store its radiance (samples that never met an emitter are exactly +0,
-            //      which the zero-filled buffer already holds)
-            if (q.any_emit) {
-                float lr, lg, lb;
-                fold_path(sc, pm, q.j, lr, lg, lb);
-                rd.sbuf[3 * (size_t)q.sidx] = lr; rd.sbuf[3 * (size_t)q.sidx + 1] = lg; rd.sbuf[3 * (size_t)q.sidx + 2] = lb;
-            }
-            st.samples += 1;
-            path_over = false;
-            htri = -1;
+        if (path_over) { path_finish(sc, rd, pm, q, st, g); path_over = false; }
+        if (g.htri < 0) {
+            const int ns = path_next_sample(p, rd, fetch, st, q, L, g);
+            if (ns == NS_EMPTY) { L.state = ST_EXIT; return; }
+            if (ns == NS_SKIP) continue;
+            if (ns == NS_TRACE) { start_ray<COUNT>(sc, L, cn); return; }
         }
-        if (htri < 0) {
-            // ---- next sample
-            const long long w = fetch();
-            if (w < 0) { L.state = ST_EXIT; return; }
-            const long long slot = w >> rd.log2_s;
-            const int ks = (int)(w & ((1ll << rd.log2_s) - 1));
-            const int k = rd.k0 + ks;
-            if (k >= rd.k1) continue;
-            const long long pixel = rd.pixel_list ? (long long)rd.pixel_list[slot] : work_to_pixel(p, slot);
-            if (pixel < 0) continue;
-            const int py = (int)(pixel / p.cols), px = (int)(pixel % p.cols);
-            q.stream = (unsigned long long)p.spp * ((unsigned long long)px + (unsigned long long)py * (unsigned long long)p.seed_stride)
-                       + (unsigned long long)k;
-            q.sidx = (uint32_t)((long long)ks * rd.slot_stride + slot);
-            q.any_emit = false; q.saved_j = -1;
-            L.r = make_ray(p, py, px);
-            if (rd.prim) {
-                // the primary ray is the same for every sample of a pixel (Lib.hs:81): its hit was traced once
-                const int2 ph = rd.prim[pixel];
-                htri = ph.x; ht = u2f((uint32_t)ph.y); q.j = 0;
-                st.primary_reused += 1;
-            } else {                                      // primary reuse off: trace it again like Lib.hs:84 does
-                q.j = -1; q.in_flight = true; start_ray<COUNT>(sc, L, cn); return;
-            }
-        }
-        // ---- shade the hit of bounce j (raytrace, Lib.hs:127-137); L.r is the ray that produced it
-        const uint32_t mat = surface_material(sc, htri);
-        pm[q.j] = (uint16_t)mat;
-        const float4 *mp = sc.mats + 3 * (size_t)mat;
-        const float4 m0 = SQT_LDG4(mp);
-        const uint32_t mflags = f2u(SQT_LDG4(mp + 2).w);
-        q.any_emit = q.any_emit || (mflags & kMatEmits);
-        const bool terminal = (q.j + 1 > p.max_depth - 1) || (p.terminate_on_black && (mflags & kMatBlack));
-        if (terminal) { path_over = true; continue; }
-        // bounceRay (Lib.hs:155-160)
-        const float x = path_draw(p, q, (uint32_t)q.j);
-        float v = 0.0f;
-        const bool scatter = m0.x < x;
-        if (scatter) { v = path_draw(p, q, (uint32_t)q.j + 1u); q.saved_r = v; q.saved_j = q.j + 1; } else q.saved_j = -1;
-        L.r = bounce_ray(sc, L.r, htri, ht, scatter, x, v);
-        q.in_flight = true;
+        if (!path_shade(sc, p, pm, q, g)) { path_over = true; continue; }
+        path_bounce(sc, p, q, L, g);
         start_ray<COUNT>(sc, L, cn);
         return;
     }
 }
+
+#if defined(__CUDACC__)
+// The same for all lanes of a warp at once (`mine`: this lane is ST_DONE): every stage is one convergent block, the
+// loop is closed by a warp vote.  Per lane the sequence of stage calls is exactly path_regen's.
+template <bool COUNT, class Fetch>
+__device__ __forceinline__ void path_regen_warp(const SceneView &sc, const RenderParams &p, const RoundInfo &rd, Fetch &fetch, PathStats &st,
+                                                PathRay &q, uint16_t *pm, TravLane &L, Counters *cn, bool mine) {
+    RegenLane g;
+    g.htri = -1; g.ht = 0.0f; g.refl = 0.0f;
+    bool fin = false, nxt = false, shd = false, bnc = false, trace = false;
+    if (mine) {
+        fin = path_consume(q, st, L, g);
+        nxt = !fin && g.htri < 0;
+        shd = g.htri >= 0;
+    }
+    for (;;) {
+        if (fin) { path_finish(sc, rd, pm, q, st, g); fin = false; nxt = true; }
+        if (nxt) {
+            const int ns = path_next_sample(p, rd, fetch, st, q, L, g);
+            if (ns == NS_EMPTY) { L.state = ST_EXIT; nxt = false; }
+            else if (ns == NS_SHADE) { nxt = false; shd = true; }
+            else if (ns == NS_TRACE) { nxt = false; trace = true; }
+        }
+        if (shd) {
+            shd = false;
+            if (path_shade(sc, p, pm, q, g)) bnc = true; else fin = true;
+        }
+        if (!__any_sync(0xffffffffu, fin || nxt)) break;
+    }
+    if (bnc) path_bounce(sc, p, q, L, g);
+    if (bnc || trace) start_ray<COUNT>(sc, L, cn);
+}
+#endif
 
 template <class Fetch>
 struct PathPolicy {
@@ -181,6 +242,13 @@ struct PathPolicy {
         : p(p_), rd(rd_), fetch(f_), st(st_), pm(pm_) { path_ray_init(q); }
     template <bool COUNT>
     SQT_HD void regen(const SceneView &sc, TravLane &L, Counters *cn) { path_regen<COUNT>(sc, p, rd, fetch, st, q, pm, L, cn); }
+#if defined(__CUDACC__)
+    static constexpr bool kWarpRegen = true;
+    template <bool COUNT>
+    __device__ __forceinline__ void regen_warp(const SceneView &sc, TravLane &L, Counters *cn, bool mine) {
+        path_regen_warp<COUNT>(sc, p, rd, fetch, st, q, pm, L, cn, mine);
+    }
+#endif
 };
 
 // avg-in-order part of renderPixel (Lib.hs:87-88): add the round's samples of one slot to the pixel's running sum,

@@ -234,3 +234,61 @@ if __name__ == "__main__":
         for burst in (4, 8, 16):
             c, r, u = simulate_pool_refill(tr256, slots, burst)
             print("pool+refill slots=%3d burst=%2d : %6.0f slots/ray  lane util %.2f" % (slots, burst, c / r, u))
+
+
+def simulate_pool_pairs(tr_all, slots=64, burst_t=4, overhead=86, pair_overhead=60, pair_round=73, min_pairs=32, max_rounds=8, c_min=16):
+    """Pool in which the triangle phase is expanded to (ray, triangle) PAIRS: the remaining triangles of all rays that
+    wait in a leaf are laid out consecutively and tested 32 at a time, one pair per lane, whichever ray they belong to."""
+    tr = tr_all[:slots]
+    pos = [0] * len(tr)
+    cost = 0
+    rays = sum(t.count("R") for t in tr)
+
+    def state(i):
+        return tr[i][pos[i]] if pos[i] < len(tr[i]) else "X"
+
+    def run_len(i):
+        n = 0
+        while pos[i] + n < len(tr[i]) and tr[i][pos[i] + n] == "L": n += 1
+        return n
+    num = den = 0
+    while True:
+        groups = {"R": [], "T": [], "E": [], "L": []}
+        for i in range(len(tr)):
+            s = state(i)
+            if s != "X": groups[s].append(i)
+        if not any(groups.values()): break
+        pairs = sum(run_len(i) for i in groups["L"])
+        cand = {k: len(groups[k]) for k in "RTE"}
+        if cand["R"] < c_min and (cand["T"] or cand["E"] or pairs): cand["R"] = 0
+        if pairs >= min_pairs or (pairs and not any(cand.values())):
+            rounds = max(1, min(max_rounds, pairs // 32))
+            budget = rounds * 32
+            used = 0
+            for i in groups["L"]:
+                n = min(run_len(i), budget - used)
+                pos[i] += n; used += n
+                if used == budget: break
+            cost += pair_overhead + pair_round * ((used + 31) // 32)
+            num += used; den += 32 * ((used + 31) // 32)
+            continue
+        kind = max(cand, key=lambda k: cand[k])
+        sel = groups[kind][:32]
+        cost += overhead
+        for b in range(burst_t if kind == "T" else 1):
+            act = [i for i in sel if state(i) == kind]
+            if not act: break
+            for i in act: pos[i] += 1
+            cost += COST[kind] + 4
+            num += len(act); den += 32
+    return cost, rays, num / max(den, 1)
+
+
+if __name__ == "__main__":
+    for slots in (64, 96):
+        c, r, u = simulate_pool(tr256, slots, 8, 4, 86)
+        print("pool        slots=%3d                : %6.0f slots/ray  lane util %.2f" % (slots, c / r, u))
+        for mp in (32, 64, 96):
+            for bt in (2, 4):
+                c, r, u = simulate_pool_pairs(tr256, slots, bt, min_pairs=mp)
+                print("pool+pairs  slots=%3d min_pairs=%3d bt=%d : %6.0f slots/ray  lane util %.2f" % (slots, mp, bt, c / r, u))
