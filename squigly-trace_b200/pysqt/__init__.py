@@ -14,7 +14,7 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ROOT = os.path.dirname(_PKG)
-LIB_B200 = os.path.join(_PKG, "libsqt_b200.so")
+LIB_B200 = os.environ.get("SQT_LIB_B200") or os.path.join(_PKG, "libsqt_b200.so")      # override: A/B builds of the kernels (development)
 LIB_HOST = os.path.join(_PKG, "libsqt_host.so")
 
 SQT_F_COUNT_WORK = 1
