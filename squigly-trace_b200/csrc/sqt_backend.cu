@@ -72,15 +72,11 @@ __device__ __forceinline__ void flush_stats(DeviceStats *ds, const PathStats &st
 struct Tune { int a_leave, b_leave, c_min; };
 
 // Warp-cooperative triangle phase.  The lanes that wait in a leaf hold (first triangle, triangles left); their
-// remaining tests are cut into UNITS of two consecutive triangles, the units of all waiting lanes are laid out
-// consecutively by a scan and executed 32 at a time, one unit per lane, whichever lane owns the ray: the owner of
-// unit p is found by a binary search over the scan (shuffles), the ray comes from the owner by shuffle.
-// A unit folds its (at most two) hits exactly like the leaf loop does; units with a hit (about one test in seventy
-// is accepted) are handed to their owner one after the other in unit order, i.e. from the leaf's last triangle to
-// its first, so every ray sees the sequence of min' applications of BIH.hs:105-109 (base-4.9 minimumBy = foldr1
-// min').  min' is "replace unless strictly farther"; without NaN that is associative, and a NaN distance (only
-// possible when t overflows) makes the fold forget everything before it -- the unit carries that as one flag, which
-// keeps the two-level fold equal to the flat one in every case.
+// remaining (ray, triangle) tests are laid out consecutively by an exclusive scan and executed 32 at a time, one
+// test per lane, whichever lane owns the ray: the owner of test p is found by a binary search over the scan
+// (shuffles), the ray comes from the owner by shuffle.  Accepted hits (about one test in seventy) are handed back
+// to the owner one after the other in test order, i.e. from the leaf's last triangle to its first, so every ray
+// sees exactly the sequence of min' applications of BIH.hs:105-109 (base-4.9 minimumBy = foldr1 min').
 // Moller-Trumbore is a pure function of (ray, triangle), so only the lane that evaluates it changes.
 template <bool COUNT>
 __device__ __forceinline__ void leaf_pairs(const SceneView &sc, TravLane &L, Counters *cn) {
@@ -89,16 +85,14 @@ __device__ __forceinline__ void leaf_pairs(const SceneView &sc, TravLane &L, Cou
     const bool in_leaf = L.state == ST_LEAF;
     const int left = in_leaf ? L.i + 1 : 0;
     const int cnt = left < 1024 ? left : 1024;            // a pathological leaf is worked off over several phases
-    const int units = (cnt + 1) >> 1;
-    int incl = units;
+    int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int v = __shfl_up_sync(FULL, incl, o);
         if (lane >= o) incl += v;
     }
+    const int start = incl - cnt;
     const int total = __shfl_sync(FULL, incl, 31);
-    // triangle of unit p's first test = first + i - 2 * (p - start) = tb - 2 * p
-    const uint32_t tb = L.child + (uint32_t)L.i + 2u * (uint32_t)(incl - units);
     for (int base = 0; base < total; base += 32) {
         const int pr = base + lane;
         int own = 0;                                       // first lane whose inclusive scan exceeds pr
@@ -111,34 +105,24 @@ __device__ __forceinline__ void leaf_pairs(const SceneView &sc, TravLane &L, Cou
         r.ox = __shfl_sync(FULL, L.r.ox, own); r.oy = __shfl_sync(FULL, L.r.oy, own); r.oz = __shfl_sync(FULL, L.r.oz, own);
         r.dx = __shfl_sync(FULL, L.r.dx, own); r.dy = __shfl_sync(FULL, L.r.dy, own); r.dz = __shfl_sync(FULL, L.r.dz, own);
         const uint32_t first = __shfl_sync(FULL, L.child, own);
-        const uint32_t ia = __shfl_sync(FULL, tb, own) - 2u * (uint32_t)pr;      // index of the unit's first triangle
-        int btri = -1;                                     // the unit's fold: (btri, bt, bdist), forget = a NaN distance occurred
-        float bt = 0.0f, bdist = 0.0f;
-        bool forget = false;
+        const int oi = __shfl_sync(FULL, L.i, own), os = __shfl_sync(FULL, start, own);
+        const uint32_t idx = first + (uint32_t)(oi - (pr - os));
+        bool hit = false;
+        float t = 0.0f, dist = 0.0f;
         if (pr < total) {
-            const int n = ia > first ? 2 : 1;              // the leaf's first triangle can be alone in its unit
-#pragma unroll 1
-            for (int k = 0; k < n; ++k) {                  // one triangle at a time: keeps the register count of the loop down
-                const TriData d = tri_load(sc, ia - (uint32_t)k);
-                int stage;
-                float t, dist;
-                if (moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage)) {
-                    forget = forget || dist != dist;
-                    if (btri < 0 || !cmp_gt(dist, bdist)) { btri = (int)(ia - (uint32_t)k); bt = t; bdist = dist; }
-                }
-                if (COUNT) { cn->mt_pass_a += stage >= 1; cn->mt_pass_u += stage >= 2; cn->mt_pass_v += stage >= 3; cn->mt_accept += stage >= 4; }
-            }
+            const TriData d = tri_load(sc, idx);
+            int stage;
+            hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
+            if (COUNT) { cn->mt_pass_a += stage >= 1; cn->mt_pass_u += stage >= 2; cn->mt_pass_v += stage >= 3; cn->mt_accept += stage >= 4; }
         }
-        unsigned hm = __ballot_sync(FULL, btri >= 0);
-        while (hm != 0u) {                                 // rare: hand each unit with a hit to its owner, in unit order
+        unsigned hm = __ballot_sync(FULL, hit);
+        while (hm != 0u) {                                 // rare: hand each accepted hit to its owner, in test order
             const int src = __ffs(hm) - 1;
             hm &= hm - 1u;
             const int o_s = __shfl_sync(FULL, own, src);
-            const float t_s = __shfl_sync(FULL, bt, src), d_s = __shfl_sync(FULL, bdist, src);
-            const int i_s = __shfl_sync(FULL, forget ? (btri | (int)0x40000000) : btri, src);
-            if (lane == o_s && ((i_s & 0x40000000) || L.cur.tri < 0 || !cmp_gt(d_s, L.cur.dist))) {
-                L.cur.tri = i_s & 0x3fffffff; L.cur.t = t_s; L.cur.dist = d_s;
-            }
+            const float t_s = __shfl_sync(FULL, t, src), d_s = __shfl_sync(FULL, dist, src);
+            const uint32_t i_s = __shfl_sync(FULL, idx, src);
+            if (lane == o_s && (L.cur.tri < 0 || !cmp_gt(d_s, L.cur.dist))) { L.cur.tri = (int)i_s; L.cur.t = t_s; L.cur.dist = d_s; }
         }
     }
     if (in_leaf) {
@@ -147,6 +131,12 @@ __device__ __forceinline__ void leaf_pairs(const SceneView &sc, TravLane &L, Cou
     }
 }
 
+// The persistent warp loop.  Every lane of the warp stays in it until all 32 have run out of work.  A round is
+// three phases, each a tight loop whose trip count is decided by a warp vote: regeneration (consume the finished
+// hit, shade, make the next ray), traversal steps (stack pops + one branch visit), triangle steps (one
+// Moller-Trumbore test).  The votes force the 32 lanes back together at every phase boundary; an ordinary
+// per-lane loop nest compiles to code where the lanes drift apart through the data-dependent traversal and
+// never reconverge (measured: 2.4 of 32 lanes active, profiles/r01_k_paths_v0_divergent.txt).
 template <class P, class = void> struct has_warp_regen : std::false_type {};
 template <class P> struct has_warp_regen<P, std::void_t<decltype(P::kWarpRegen)>> : std::true_type {};
 
@@ -283,6 +273,9 @@ __global__ void __launch_bounds__(128, SQT_WL_MIN_BLOCKS) k_paths(SceneView sc, 
 #define SQT_POOL_MIN_BLOCKS 8
 #endif
 struct PoolTune { int burst_t, burst_l, c_min; };
+#ifndef SQT_POOL_TRI_UNROLL
+#define SQT_POOL_TRI_UNROLL 2
+#endif
 
 // 16 words = 64 B per ray in shared memory.  PF_MI holds `meta` while the ray descends / enters and `i` while it is in a
 // leaf; PF_FLAGS = state | safe << 8 | sgn << 16 | sp << 24.  (4 warps x 64 rays x 64 B + lists = 16.5 KB per CTA, so
@@ -300,7 +293,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t *pool = pool_smem + warp * (P * PF_WORDS + 32);
     uint32_t *sel = pool + P * PF_WORDS;
-    const long long gslot0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * P;
+    const int gslot0 = (int)((blockIdx.x * (blockDim.x >> 5) + warp) * P);     // < 2^31: at most a few hundred thousand pool slots exist
 #define PW(f, slot) pool[(f) * P + (slot)]
     Counters cn = {};
     PathStats st = {0, 0, 0};
@@ -362,8 +355,10 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
                 L.state = ST_LEAF;
             } else L.state = ST_EXIT;
-            for (int b = 0; b < tn.burst_l; ++b) {
-                if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, &cn);
+            for (int b = 0; b < tn.burst_l; b += SQT_POOL_TRI_UNROLL) {  // several tests per vote
+#pragma unroll
+                for (int u = 0; u < SQT_POOL_TRI_UNROLL; ++u)
+                    if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, &cn);
                 if (!__any_sync(FULL, L.state == ST_LEAF)) break;
             }
             if (act) {
@@ -574,7 +569,7 @@ struct sqt_ctx {
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
     Tune tune = {12, 0, 12};
     int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
-    PoolTune pool_tune = {4, 8, 16};
+    PoolTune pool_tune = {4, 16, 16};
     int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1
     uint32_t *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0;
     // group
