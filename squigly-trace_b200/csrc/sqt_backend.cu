@@ -286,7 +286,7 @@ enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_
 
 template <bool COUNT, int K>
 __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, PoolTune tn,
-                                                    uint32_t *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath) {
+                                                    uint32_t *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath, int stack_stride) {
     extern __shared__ uint32_t pool_smem[];
     constexpr int P = 32 * K;
     const unsigned FULL = 0xffffffffu;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         const bool act = lane < n_sel;
         const int slot = act ? (int)sel[lane] : 0;
         TravLane L;
-        L.stack = gstack + (size_t)(gslot0 + slot) * kStackWords;
+        L.stack = gstack + (size_t)(gslot0 + slot) * (size_t)stack_stride;
         if (kind == 0) {
             // ---- triangle tests
             if (act) {
@@ -792,7 +792,12 @@ static int launch_pool(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd,
         CU(cudaMalloc(&ctx->d_gpath, (size_t)cap * 2 * sizeof(uint4)));
         ctx->cap_pool_slots = cap;
     }
-    kern<<<(int)grid, 128, smem, ctx->stream>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->pool_tune, ctx->d_gstack, ctx->d_gpm, ctx->d_gpath);
+    // a ray's stack holds at most one 3-word entry per branch on a root-to-leaf path: pack the slots' stacks that tightly
+    // (32-byte granules) so that the stacks of all resident slots stay in L2
+    int stride = (int)((3u * ctx->tree_height + 7u) & ~7u);
+    if (stride > kStackWords) stride = kStackWords;
+    if (stride < 8) stride = 8;
+    kern<<<(int)grid, 128, smem, ctx->stream>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->pool_tune, ctx->d_gstack, ctx->d_gpm, ctx->d_gpath, stride);
     CU(cudaGetLastError());
     return SQT_OK;
 }
