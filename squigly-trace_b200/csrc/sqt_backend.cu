@@ -310,31 +310,32 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
     __syncwarp(FULL);
     const unsigned lt_mask = (1u << lane) - 1u;
     for (;;) {
-        // ---- census of the pool
-        int sk[K];
-        int n_t = 0, n_e = 0, n_l = 0, n_r = 0;
+        // ---- census of the pool: every lane classifies its K slots (kind 0 = traversal, 1 = leaf entry, 2 = triangle,
+        //      3 = regeneration, 7 = exited), packs one count byte per kind and the warp adds the packed words (REDUX)
+        int kk[K];
+        unsigned packed = 0u;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            sk[k] = (int)(PW(PF_FLAGS, lane + 32 * k) & 0xffu);
-            n_t += __popc(__ballot_sync(FULL, sk[k] == ST_DESC || sk[k] == ST_RET));
-            n_e += __popc(__ballot_sync(FULL, sk[k] == ST_ENTER));
-            n_l += __popc(__ballot_sync(FULL, sk[k] == ST_LEAF));
-            n_r += __popc(__ballot_sync(FULL, sk[k] == ST_DONE));
+            const unsigned sst = PW(PF_FLAGS, lane + 32 * k) & 0xffu;
+            // ST_DONE 0 -> 3, ST_DESC 1 -> 0, ST_LEAF 2 -> 2, ST_RET 3 -> 0, ST_EXIT 4 -> 7, ST_ENTER 5 -> 1
+            const int kd = (int)(0x170203u >> (4u * sst)) & 7;
+            kk[k] = kd;
+            packed += kd == 7 ? 0u : (1u << (8 * kd));
         }
-        if ((n_t | n_e | n_l | n_r) == 0) break;                           // every slot is ST_EXIT
+        packed = __reduce_add_sync(FULL, packed);
+        if (packed == 0u) break;                                            // every slot is ST_EXIT
+        const int n_t = (int)(packed & 0xffu), n_e = (int)((packed >> 8) & 0xffu), n_l = (int)((packed >> 16) & 0xffu), n_r = (int)(packed >> 24);
         // ---- pick the kind of step with the most waiting rays (regeneration only in batches)
-        const int c_r = (n_r >= tn.c_min || (n_t | n_e | n_l) == 0) ? n_r : 0;
-        int kind = 0, best = n_l;                                           // 0 = triangle, 1 = traversal, 2 = enter, 3 = regen
-        if (n_t > best) { kind = 1; best = n_t; }
-        if (n_e > best) { kind = 2; best = n_e; }
+        const int c_r = (n_r >= tn.c_min || (packed & 0x00ffffffu) == 0u) ? n_r : 0;
+        int kind = 2, best = n_l;
+        if (n_t > best) { kind = 0; best = n_t; }
+        if (n_e > best) { kind = 1; best = n_e; }
         if (c_r > best) { kind = 3; best = c_r; }
-        if (best == 0) { kind = 3; }                                        // only finished rays below c_min are left: cannot happen (c_r covers it)
         // ---- gather up to 32 rays of that kind onto the lanes
         int base = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const bool mine = kind == 0 ? sk[k] == ST_LEAF
-                            : (kind == 1 ? (sk[k] == ST_DESC || sk[k] == ST_RET) : (kind == 2 ? sk[k] == ST_ENTER : sk[k] == ST_DONE));
+            const bool mine = kk[k] == kind;
             const unsigned b = __ballot_sync(FULL, mine);
             const int rank = base + __popc(b & lt_mask);
             if (mine && rank < 32) sel[rank] = (uint32_t)(lane + 32 * k);
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         const int slot = act ? (int)sel[lane] : 0;
         TravLane L;
         L.stack = gstack + (size_t)(gslot0 + slot) * (size_t)stack_stride;
-        if (kind == 0) {
+        if (kind == 2) {
             // ---- triangle tests
             if (act) {
                 L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
                 if (L.state != ST_LEAF) PW(PF_FLAGS, slot) = (PW(PF_FLAGS, slot) & ~0xffu) | (uint32_t)L.state;
             }
-        } else if (kind == 1) {
+        } else if (kind == 0) {
             // ---- traversal steps: stack pops + branch visits
             uint32_t fl = 0u;
             if (act) {
@@ -378,7 +379,9 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 fl = PW(PF_FLAGS, slot);
                 L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
             } else L.state = ST_EXIT;
-            for (int b = 0; b < tn.burst_t; ++b) {
+            for (int b = 0; b < tn.burst_t; b += 2) {                     // two steps per vote
+                if (L.state == ST_RET) ret_step(sc, L);
+                if (L.state == ST_DESC) desc_step<COUNT>(sc, L, &cn);
                 if (L.state == ST_RET) ret_step(sc, L);
                 if (L.state == ST_DESC) desc_step<COUNT>(sc, L, &cn);
                 if (!__any_sync(FULL, L.state == ST_DESC || L.state == ST_RET)) break;
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
                 PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
             }
-        } else if (kind == 2) {
+        } else if (kind == 1) {
             // ---- leaf entry: record fetch + conservative culling
             if (act) {
                 L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
