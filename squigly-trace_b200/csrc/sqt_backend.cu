@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         const bool act = lane < n_sel;
         const int slot = act ? (int)sel[lane] : 0;
         TravLane L;
-        L.stack = gstack + (size_t)(gslot0 + slot) * (size_t)stack_stride;
+        L.stack = nullptr;                                                  // only traversal steps touch the stack
         if (kind == 2) {
             // ---- triangle tests
             if (act) {
@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         } else if (kind == 0) {
             // ---- traversal steps: stack pops + branch visits
             uint32_t fl = 0u;
+            L.stack = gstack + (size_t)(gslot0 + slot) * (size_t)stack_stride;
             if (act) {
                 L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
                 L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
