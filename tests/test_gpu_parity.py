@@ -169,6 +169,33 @@ def test_degenerate_split_and_empty_leaves(gpu_ctx):
     assert_same_hits(gpu_ctx.intersect_batch(org, dirs), osc.intersect_batch(org, dirs), "degenerate")
 
 
+@pytest.mark.parametrize("tune", ["12,0,12", "8,1,8"])
+def test_long_leaf_with_duplicate_triangles(monkeypatch, tune):
+    """A leaf of 2600 triangles (longer than the 1024 tests the warp-cooperative triangle phase takes from one leaf per
+    phase) in which every triangle exists four times: all four copies are hit at exactly the same distance, so the
+    result depends on the order of the min' fold (BIH.hs:105-109: the first of the minimal ones wins).  Both triangle
+    phases -- tests spread over all lanes (b_leave = 0) and one test per lane and step -- must reproduce it."""
+    monkeypatch.setenv("SQT_TUNE", tune)
+    rng = np.random.default_rng(21)
+    n0, copies = 650, 4
+    base = rng.uniform(-1, 1, (n0, 1, 3)).astype(np.float32) * np.array([0, 1, 1], np.float32)   # x centroid identical
+    offs = np.array([[0.3, 0, 0], [-0.15, 0.2, 0.1], [-0.15, -0.2, -0.1]], np.float32)
+    v9 = (base * np.float32(2e-3) + offs[None]).reshape(n0, 9)                 # x extent dominates: the split axis is x
+    v9 = np.tile(v9, (copies, 1))[rng.permutation(n0 * copies)]
+    mats = np.array([[0, .5, .5, .5, 0, 0, 0, 0]], np.float32)
+    osc, hs = build_pair(v9, np.zeros(len(v9), np.int32), mats)
+    assert hs.stats()["longest_leaf"] == n0 * copies
+    ctx = pysqt.Context(0)
+    ctx.upload(hs)
+    org = rng.uniform(-1, 1, (6000, 3)).astype(np.float32)
+    target = rng.uniform([-0.1, -0.12, -0.06], [0.2, 0.12, 0.06], (6000, 3)).astype(np.float32)   # inside the pile of triangles
+    dirs = target - org
+    got, ref = ctx.intersect_batch(org, dirs), osc.intersect_batch(org, dirs)
+    assert (ref[0] >= 0).mean() > 0.3
+    assert_same_hits(got, ref, "long leaf, duplicates, SQT_TUNE=" + tune)
+    ctx.close()
+
+
 @pytest.mark.parametrize("gen,n", [("cornell", 10000), ("soup", 60000), ("mesh", 80000)])
 def test_synthetic_scenes_bit_exact(gpu_ctx, gen, n):
     v9, mi, mats = {"cornell": scenes.cornell_box, "soup": scenes.triangle_soup, "mesh": scenes.subdivided_mesh}[gen](n)
