@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(128, SQT_WL_MIN_BLOCKS) k_paths(SceneView sc, 
 // that one kind of step with (nearly) all lanes active, and writes the rays back.  With one ray per lane at most
 // ~10 of 32 lanes share a step kind at any time (tools/sched_sim.py); regrouping rays lifts that limit.
 #ifndef SQT_POOL_MIN_BLOCKS
-#define SQT_POOL_MIN_BLOCKS 8
+#define SQT_POOL_MIN_BLOCKS 9
 #endif
 struct PoolTune { int burst_t, burst_l, c_min; };
 #ifndef SQT_POOL_TRI_UNROLL
