@@ -63,17 +63,16 @@ namespace sqt {
 // edge, used only by the conservative leaf culling below (never by the reference algorithm):
 //   b0 = (lo.x, lo.y, lo.z, hi.x)   b1 = (hi.y, hi.z, longest edge E, first triangle as u32 bits)
 //        lmeta additionally carries the split axis in bits 27..28
-// Traversal stack entries are 3 words:
-//   phase A (near subtree in flight): { isClose plane (rmin if left-to-right else lmax), far child ref,
-//                                       far meta | axis << 27 | kLtr if left-to-right }
-//   phase B (near hit parked, far subtree in flight): { t bits, dist bits, tri | kPhaseB }
+// Traversal stack entries (the top word tells them apart):
+//   phase A (near subtree in flight), 1 word : index of the branch (< 2^30, so kPhaseB is clear); plane, far child and
+//                                              its meta are re-read from the node when the near subtree returns
+//   phase B (near hit parked, far subtree in flight), 3 words : { t bits, dist bits, tri | kPhaseB }
 constexpr uint32_t kLeaf = 0x80000000u;
 constexpr uint32_t kPhaseB = 0x40000000u;
-constexpr uint32_t kLtr = 0x20000000u;
 constexpr uint32_t kAxisShift = 27;
 constexpr uint32_t kCountMask = 0x07ffffffu;
 constexpr int kNodeQuads = 4;
-constexpr int kStackWords = 3 * 48;            // one 3-word entry per tree level at most
+constexpr int kStackWords = 3 * 48;            // at most one entry (1 or 3 words) per tree level
 #ifndef SQT_MAX_DEPTH
 #define SQT_MAX_DEPTH 64
 #endif
@@ -366,12 +365,9 @@ SQT_HD void desc_step(const SceneView &sc, TravLane &L, Counters *cn) {
     const bool both = hit_l && hit_r;
     const bool go_left = both ? ltr : hit_l;                                // near child first (BIH.hs:124-126)
     const uint32_t lm = lmeta & (kLeaf | kCountMask);
-    if (both) {                                                             // phase A frame: what ret_step needs later
-        const float lmax = sel3((int)ax, q1.z, q1.w, q2.x), rmin = sel3((int)ax, q2.y, q2.z, q2.w);
-        L.stack[L.sp] = f2u(ltr ? rmin : lmax);
-        L.stack[L.sp + 1] = ltr ? right : left;
-        L.stack[L.sp + 2] = (ltr ? rmeta : lm) | (ax << kAxisShift) | (ltr ? kLtr : 0u);
-        L.sp += 3;
+    if (both) {                                 // phase A frame: ONE word, this branch; ret_step re-reads plane and far child from the node
+        L.stack[L.sp] = L.child;
+        L.sp += 1;
     }
     L.child = go_left ? left : right;
     L.meta = go_left ? lm : rmeta;
@@ -405,28 +401,41 @@ SQT_HD void tri_step(const SceneView &sc, TravLane &L, Counters *cn) {
     const TriData d = tri_load(sc, L.child + (uint32_t)L.i);
     tri_apply<COUNT>(L, d, cn);
 }
-// A subtree returned `cur`: pop entries until one of them sends the lane into a far subtree (-> ST_DESC) or
-// the stack is empty (-> ST_DONE).  Pops that only merge or propagate are a handful of instructions each.
+// A subtree returned `cur`: pop entries until one of them sends the lane into a far subtree (-> ST_DESC / ST_ENTER) or
+// the stack is empty (-> ST_DONE).  Two kinds of entry, told apart by kPhaseB in the top word:
+//   phase A, 1 word  : index of a branch whose NEAR subtree just returned (both children were hit);
+//   phase B, 3 words : (t, dist, tri | kPhaseB), the parked near hit of a branch whose FAR subtree just returned.
+// Keeping phase A at one word (instead of caching plane / far child / meta in the entry) cuts the stack traffic to a
+// third; the branch's node is re-read on the way back -- it was read on the way down and is normally still in L1/L2.
 SQT_HD void ret_step(const SceneView &sc, TravLane &L) {
     for (;;) {
         if (L.sp == 0) { finish_ray(sc, L); return; }
-        const uint32_t w0 = L.stack[L.sp - 3], w1 = L.stack[L.sp - 2], w2 = L.stack[L.sp - 1];
-        L.sp -= 3;
-        if (w2 & kPhaseB) {                                                 // far subtree returned: min' near far
-            if (L.cur.tri < 0 || !cmp_gt(u2f(w1), L.cur.dist)) { L.cur.tri = (int)(w2 & ~kPhaseB); L.cur.dist = u2f(w1); L.cur.t = u2f(w0); }
+        const uint32_t w = L.stack[L.sp - 1];
+        if (w & kPhaseB) {                                                  // far subtree returned: min' near far
+            const uint32_t w0 = L.stack[L.sp - 3], w1 = L.stack[L.sp - 2];
+            L.sp -= 3;
+            if (L.cur.tri < 0 || !cmp_gt(u2f(w1), L.cur.dist)) { L.cur.tri = (int)(w & ~kPhaseB); L.cur.dist = u2f(w1); L.cur.t = u2f(w0); }
             continue;
         }
-        // near subtree returned
+        L.sp -= 1;
+        // near subtree of branch w returned
+        const float4 *np = sc.nodes + kNodeQuads * (size_t)w;
+        const float4 q3 = SQT_LDG4(np + 3);
+        const uint32_t lmeta = f2u(q3.z);
+        const int ax = (int)((lmeta >> kAxisShift) & 3u);
+        const bool ltr = ((L.sgn >> ax) & 1u) != 0u;                        // BIH.hs:127: the near child was left iff leftToRight
         if (L.cur.tri >= 0) {
-            const int ax = (int)((w2 >> kAxisShift) & 3u);
+            const float4 q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
+            const float plane = ltr ? sel3(ax, q2.y, q2.z, q2.w) : sel3(ax, q1.z, q1.w, q2.x);      // rmin : lmax
             const float p = XADD(sel3(ax, L.r.ox, L.r.oy, L.r.oz), XMUL(L.cur.t, sel3(ax, L.r.dx, L.r.dy, L.r.dz)));   // intersectPoint on ax
-            const bool close = (w2 & kLtr) ? (p < u2f(w0)) : (p > u2f(w0));  // BIH.hs:121-123
+            const bool close = ltr ? (p < plane) : (p > plane);             // BIH.hs:121-123
             if (close) continue;
             L.stack[L.sp] = f2u(L.cur.t); L.stack[L.sp + 1] = f2u(L.cur.dist); L.stack[L.sp + 2] = (uint32_t)L.cur.tri | kPhaseB;
             L.sp += 3;
         }
-        L.child = w1; L.meta = w2 & (kLeaf | kCountMask);
-        L.state = (w2 & kLeaf) ? ST_ENTER : ST_DESC;
+        L.child = ltr ? f2u(q3.y) : f2u(q3.x);
+        L.meta = ltr ? f2u(q3.w) : (lmeta & (kLeaf | kCountMask));
+        L.state = (L.meta & kLeaf) ? ST_ENTER : ST_DESC;
         return;
     }
 }
