@@ -286,7 +286,7 @@ enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_
 
 template <bool COUNT, int K>
 __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, PoolTune tn,
-                                                    uint32_t *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath, int stack_stride) {
+                                                    uint32_t *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath, int stack_stride, int pm_stride) {
     extern __shared__ uint32_t pool_smem[];
     constexpr int P = 32 * K;
     const unsigned FULL = 0xffffffffu;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         } else if (kind == 0) {
             // ---- traversal steps: stack pops + branch visits
             uint32_t fl = 0u;
-            L.stack = gstack + (size_t)(gslot0 + slot) * (size_t)stack_stride;
+            L.stack = gstack + (size_t)gslot0 * (size_t)stack_stride + 8 * slot;     // the warp's P stacks, interleaved in 32-byte granules
             if (act) {
                 L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
                 L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
             } else L.state = ST_EXIT;
             for (int b = 0; b < tn.burst_t; ++b) {                        // (two steps per vote: the second copy of the step costs more than the vote, -16 %)
-                if (L.state == ST_RET) ret_step(sc, L);
-                if (L.state == ST_DESC) desc_step<COUNT>(sc, L, &cn);
+                if (L.state == ST_RET) ret_step<8 * P>(sc, L);
+                if (L.state == ST_DESC) desc_step<COUNT, 8 * P>(sc, L, &cn);
                 if (!__any_sync(FULL, L.state == ST_DESC || L.state == ST_RET)) break;
             }
             if (act) {
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 q.saved_r = u2f(g1.x); q.saved_j = (int)(pf & 0xffffu) - 1;
                 q.any_emit = ((pf >> 16) & 1u) != 0u; q.in_flight = ((pf >> 17) & 1u) != 0u;
             }
-            path_regen_warp<COUNT>(sc, p, rd, fetch, st, q, gpm + (size_t)(gslot0 + slot) * SQT_MAX_DEPTH, L, &cn, act);
+            path_regen_warp<COUNT>(sc, p, rd, fetch, st, q, gpm + (size_t)(gslot0 + slot) * (size_t)pm_stride, L, &cn, act);
             if (act) {
                 PW(PF_OX, slot) = f2u(L.r.ox); PW(PF_OY, slot) = f2u(L.r.oy); PW(PF_OZ, slot) = f2u(L.r.oz);
                 PW(PF_DX, slot) = f2u(L.r.dx); PW(PF_DY, slot) = f2u(L.r.dy); PW(PF_DZ, slot) = f2u(L.r.dz);
@@ -799,7 +799,10 @@ static int launch_pool(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd,
     int stride = (int)((3u * ctx->tree_height + 7u) & ~7u);
     if (stride > kStackWords) stride = kStackWords;
     if (stride < 8) stride = 8;
-    kern<<<(int)grid, 128, smem, ctx->stream>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->pool_tune, ctx->d_gstack, ctx->d_gpm, ctx->d_gpath, stride);
+    // the per-path material list of a slot: max_depth entries, packed (16-byte granules) for the same reason
+    int pm_stride = (d.max_depth + 7) & ~7;
+    if (pm_stride > SQT_MAX_DEPTH) pm_stride = SQT_MAX_DEPTH;
+    kern<<<(int)grid, 128, smem, ctx->stream>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->pool_tune, ctx->d_gstack, ctx->d_gpm, ctx->d_gpath, stride, pm_stride);
     CU(cudaGetLastError());
     return SQT_OK;
 }

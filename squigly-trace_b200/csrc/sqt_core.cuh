@@ -351,7 +351,16 @@ SQT_HD void enter_step(const SceneView &sc, TravLane &L, Counters *cn) {
     L.state = ST_LEAF;
 }
 
-template <bool COUNT>
+// Word w of the lane's stack.  PLANE = 8: a plain array (lane-private local memory).  PLANE > 8: the stacks of a group of
+// PLANE/8 rays are interleaved in 32-byte granules -- granule g of every ray of the group is contiguous -- so that the few
+// granules in use (a stack is usually < 8 words deep) of all rays share cache lines instead of each ray owning lines of its
+// own (k_paths_pool: the stacks of all resident pool slots then fit L2).
+template <int PLANE>
+SQT_HD uint32_t &stack_word(TravLane &L, int w) {
+    return L.stack[PLANE == 8 ? w : (w >> 3) * PLANE + (w & 7)];
+}
+
+template <bool COUNT, int PLANE = 8>
 SQT_HD void desc_step(const SceneView &sc, TravLane &L, Counters *cn) {
     const float4 *np = sc.nodes + kNodeQuads * (size_t)L.child;
     const float4 q0 = SQT_LDG4(np), q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2), q3 = SQT_LDG4(np + 3);
@@ -366,7 +375,7 @@ SQT_HD void desc_step(const SceneView &sc, TravLane &L, Counters *cn) {
     const bool go_left = both ? ltr : hit_l;                                // near child first (BIH.hs:124-126)
     const uint32_t lm = lmeta & (kLeaf | kCountMask);
     if (both) {                                 // phase A frame: ONE word, this branch; ret_step re-reads plane and far child from the node
-        L.stack[L.sp] = L.child;
+        stack_word<PLANE>(L, L.sp) = L.child;
         L.sp += 1;
     }
     L.child = go_left ? left : right;
@@ -407,12 +416,13 @@ SQT_HD void tri_step(const SceneView &sc, TravLane &L, Counters *cn) {
 //   phase B, 3 words : (t, dist, tri | kPhaseB), the parked near hit of a branch whose FAR subtree just returned.
 // Keeping phase A at one word (instead of caching plane / far child / meta in the entry) cuts the stack traffic to a
 // third; the branch's node is re-read on the way back -- it was read on the way down and is normally still in L1/L2.
+template <int PLANE = 8>
 SQT_HD void ret_step(const SceneView &sc, TravLane &L) {
     for (;;) {
         if (L.sp == 0) { finish_ray(sc, L); return; }
-        const uint32_t w = L.stack[L.sp - 1];
+        const uint32_t w = stack_word<PLANE>(L, L.sp - 1);
         if (w & kPhaseB) {                                                  // far subtree returned: min' near far
-            const uint32_t w0 = L.stack[L.sp - 3], w1 = L.stack[L.sp - 2];
+            const uint32_t w0 = stack_word<PLANE>(L, L.sp - 3), w1 = stack_word<PLANE>(L, L.sp - 2);
             L.sp -= 3;
             if (L.cur.tri < 0 || !cmp_gt(u2f(w1), L.cur.dist)) { L.cur.tri = (int)(w & ~kPhaseB); L.cur.dist = u2f(w1); L.cur.t = u2f(w0); }
             continue;
@@ -430,7 +440,8 @@ SQT_HD void ret_step(const SceneView &sc, TravLane &L) {
             const float p = XADD(sel3(ax, L.r.ox, L.r.oy, L.r.oz), XMUL(L.cur.t, sel3(ax, L.r.dx, L.r.dy, L.r.dz)));   // intersectPoint on ax
             const bool close = ltr ? (p < plane) : (p > plane);             // BIH.hs:121-123
             if (close) continue;
-            L.stack[L.sp] = f2u(L.cur.t); L.stack[L.sp + 1] = f2u(L.cur.dist); L.stack[L.sp + 2] = (uint32_t)L.cur.tri | kPhaseB;
+            stack_word<PLANE>(L, L.sp) = f2u(L.cur.t); stack_word<PLANE>(L, L.sp + 1) = f2u(L.cur.dist);
+            stack_word<PLANE>(L, L.sp + 2) = (uint32_t)L.cur.tri | kPhaseB;
             L.sp += 3;
         }
         L.child = ltr ? f2u(q3.y) : f2u(q3.x);
