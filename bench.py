@@ -34,7 +34,7 @@ for p in (ROOT, PKG):
 WIDTH, HEIGHT, SPP, DEPTH, SEED = 1920, 1080, 1024, 8, 0
 DATA = os.path.join(ROOT, "data")
 WORKLOAD = "data/scene.obj 1920x1080 1024spp depth8"
-NCU_DRAM_BYTES_PER_LAUNCH = 10606641000 + 37847887000    # profiles/r01_k_paths_v6_pool.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 205336064 + 591681024        # profiles/r01_k_paths_v7_pool.txt
 
 
 class ClockSampler:
@@ -259,8 +259,8 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "fp32", "kernel": "k_paths_pool", "achieved": achieved, "peak": fp32_peak / 1e3, "unit": "TFLOP/s",
                 "frac": achieved / (fp32_peak / 1e3), "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 64-spp k_paths_pool launch (the bench issues 16 such "
-                                  "launches per frame), ncu --set full, profiles/r01_k_paths_v6_pool.txt; almost all of it is write-back of "
-                                  "the per-slot traversal stacks, which live in global memory in the pool kernel",
+                                  "launches per frame), ncu --set full, profiles/r01_k_paths_v7_pool.txt: sample-buffer writes and first-touch "
+                                  "fills; scene, pool-slot stacks and path state are L1/L2 resident",
                 "peak_source": "measured live: non-fused FADD/FMUL issue rate of this GPU (sqt_measure_fp32_peak); FMA contraction is "
                                "forbidden on the bit-exact path, so this is the FP32 ceiling (MEASURED_PEAKS.json has no FP32 figure)",
                 "kernel_ms": k_ms, "kernel_ms_note": "all k_paths + k_accumulate launches of one frame (one pair per 64-spp round)",
