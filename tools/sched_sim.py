@@ -134,7 +134,7 @@ def simulate(tr, policy, **kw):
     return cost, rays
 
 
-if __name__ == "__main__":
+def study_phases():
     tr = traces()
     tot = sum(len(t) for t in tr)
     print("lanes", len(tr), "steps", tot, {k: sum(t.count(k) for t in tr) for k in "RTEL"})
@@ -180,7 +180,7 @@ def simulate_pool(tr_all, slots=64, burst_l=4, burst_t=2, overhead=86, pick="max
     return cost, rays, util_num / max(util_den, 1)
 
 
-if __name__ == "__main__":
+def study_pool():
     tr128 = traces(n_lanes=128, pixels_per_lane=2, spp=6)
     ideal = sum(COST[c] for t in tr128 for c in t) / 32
     rays = sum(t.count("R") for t in tr128)
@@ -228,7 +228,7 @@ def simulate_pool_refill(tr_all, slots=64, burst=8, overhead=86, refill_cost=30,
     return cost, rays, num / max(den, 1)
 
 
-if __name__ == "__main__":
+def study_refill():
     tr256 = traces(n_lanes=256, pixels_per_lane=1, spp=6)
     for slots in (64, 96, 128, 256):
         for burst in (4, 8, 16):
@@ -284,7 +284,8 @@ def simulate_pool_pairs(tr_all, slots=64, burst_t=4, overhead=86, pair_overhead=
     return cost, rays, num / max(den, 1)
 
 
-if __name__ == "__main__":
+def study_pairs():
+    tr256 = traces(n_lanes=256, pixels_per_lane=1, spp=6)
     for slots in (64, 96):
         c, r, u = simulate_pool(tr256, slots, 8, 4, 86)
         print("pool        slots=%3d                : %6.0f slots/ray  lane util %.2f" % (slots, c / r, u))
@@ -292,3 +293,73 @@ if __name__ == "__main__":
             for bt in (2, 4):
                 c, r, u = simulate_pool_pairs(tr256, slots, bt, min_pairs=mp)
                 print("pool+pairs  slots=%3d min_pairs=%3d bt=%d : %6.0f slots/ray  lane util %.2f" % (slots, mp, bt, c / r, u))
+
+
+def simulate_warp_loop_pairs(tr_all, lanes=32, a_leave=12, c_min=12, pairs=True, pair_round=125, pair_overhead=30, vote=6, outer=30, b_leave=1):
+    """One ray per lane (warp_loop) with the WARP-COOPERATIVE triangle phase: all triangle tests of the lanes that wait in a
+    leaf are executed 32 at a time, whichever lane owns the ray (leaf_pairs in csrc/sqt_backend.cu); pairs=False is the old
+    one-test-per-lane-and-step phase.  pair_round = instructions per 32 tests (measured: ~95 search/shuffle/hand-over + ~97
+    Moller-Trumbore, but only ~60 % of the latter when few lanes pass the guards)."""
+    tr = tr_all[:lanes]
+    pos = [0] * len(tr)
+    rays = sum(t.count("R") for t in tr)
+    cost = 0
+
+    def state(i):
+        return tr[i][pos[i]] if pos[i] < len(tr[i]) else "X"
+
+    def run_len(i):
+        n = 0
+        while pos[i] + n < len(tr[i]) and tr[i][pos[i] + n] == "L": n += 1
+        return n
+
+    def lanes_in(k):
+        return [i for i in range(len(tr)) if state(i) == k]
+    while any(state(i) != "X" for i in range(len(tr))):
+        cost += outer
+        done, busy = lanes_in("R"), [i for i in range(len(tr)) if state(i) in "TEL"]
+        if done and (len(done) >= c_min or not busy):
+            for i in done: pos[i] += 1
+            cost += COST["R"]
+        first = True
+        while True:
+            t = lanes_in("T")
+            if not t or (not first and len(t) <= a_leave and (lanes_in("E") or lanes_in("L"))): break
+            first = False
+            for i in t: pos[i] += 1
+            cost += COST["T"] + vote
+        e = lanes_in("E")
+        if e:
+            for i in e: pos[i] += 1
+            cost += COST["E"] + vote
+        if pairs:
+            ls = lanes_in("L")
+            n = sum(run_len(i) for i in ls)
+            if n:
+                for i in ls: pos[i] += run_len(i)
+                cost += pair_overhead + pair_round * ((n + 31) // 32)
+        else:
+            while True:
+                ls = lanes_in("L")
+                if not ls or (len(ls) <= b_leave and lanes_in("T")): break
+                for i in ls: pos[i] += 1
+                cost += COST["L"] + vote
+    return cost, rays
+
+
+def study_warp_loop_pairs():
+    tr = traces(n_lanes=32, pixels_per_lane=1, spp=6)
+    c, r = simulate_warp_loop_pairs(tr, pairs=False, a_leave=8, c_min=8)
+    print("warp_loop, one test per lane and step       : %6.0f slots/ray" % (c / r))
+    for a in (4, 8, 12, 16):
+        for pr in (90, 125, 190):
+            c, r = simulate_warp_loop_pairs(tr, a_leave=a, c_min=8, pair_round=pr)
+            print("warp_loop + leaf_pairs a_leave=%2d pair_round=%3d : %6.0f slots/ray" % (a, pr, c / r))
+
+
+STUDIES = {"phases": study_phases, "pool": study_pool, "refill": study_refill, "pairs": study_pairs, "warp_pairs": study_warp_loop_pairs}
+
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or list(STUDIES)):
+        print("==== " + name)
+        STUDIES[name]()
