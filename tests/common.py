@@ -61,6 +61,17 @@ class Emu:
         return tri, dist, pt, dict(branch_visits=int(cn[0]), child_box_tests=int(cn[1]), tri_tests=int(cn[2]), rays=int(cn[3]),
                                    leaves_culled=int(cn[4]))
 
+    def intersect_batch_interleaved(self, org, dirs):
+        """64 rays at a time stepped round-robin with their stacks interleaved like the pool kernel's (see emu.cpp)."""
+        org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)
+        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = len(org)
+        tri = np.zeros(n, np.int32); dist = np.zeros(n, np.float32)
+        E = emu_lib()
+        E.emu_intersect_batch_interleaved.restype = C.c_int
+        bad = E.emu_intersect_batch_interleaved(self.h, _p(org), _p(dirs), C.c_longlong(n), _p(tri), _p(dist))
+        return tri, dist, bad
+
     def set_leaf_cull(self, on):
         emu_lib().emu_set_leaf_cull(self.h, 1 if on else 0)
 

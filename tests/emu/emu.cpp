@@ -71,6 +71,49 @@ void emu_intersect_batch(emu_scene *s, const float *org, const float *dir, long 
     if (counters4) { counters4[0] = cn.branch_visits; counters4[1] = cn.child_box_tests; counters4[2] = cn.tri_tests; counters4[3] = cn.rays; counters4[4] = cn.leaves_culled; }
 }
 
+// The pool kernel's stack layout on the host: groups of 64 rays share ONE region in which their stacks are interleaved in
+// 32-byte granules (stack_word<512>), stride = 3 * height words rounded to 8 as launch_pool computes it.  The 64 rays are
+// stepped round-robin, one unit step each, so that an addressing error (overlap between slots, a stride too small) would
+// corrupt a neighbour's stack while it is live.  Canary words behind the region catch overruns.  Returns 0, or 1 if a
+// canary was overwritten.
+int emu_intersect_batch_interleaved(emu_scene *s, const float *org, const float *dir, long long n, int *tri_out, float *dist_out) {
+    constexpr int P = 64;
+    int stride = (int)((3u * s->lay.height + 7u) & ~7u);
+    if (stride > kStackWords) stride = kStackWords;
+    if (stride < 8) stride = 8;
+    std::vector<uint32_t> region((size_t)P * stride + 64, 0xdeadbeefu);
+    Counters cn = {};
+    int bad = 0;
+    for (long long base = 0; base < n; base += P) {
+        const int m = (int)std::min<long long>(P, n - base);
+        TravLane L[P];
+        for (int k = 0; k < m; ++k) {
+            L[k].stack = region.data() + 8 * k;
+            L[k].r = Ray{org[3 * (base + k)], org[3 * (base + k) + 1], org[3 * (base + k) + 2], dir[3 * (base + k)], dir[3 * (base + k) + 1], dir[3 * (base + k) + 2]};
+            start_ray<false>(s->view, L[k], &cn);
+        }
+        for (bool any = true; any;) {
+            any = false;
+            for (int k = 0; k < m; ++k) {
+                TravLane &l = L[k];
+                if (l.state == ST_DONE) continue;
+                any = true;
+                if (l.state == ST_RET) ret_step<8 * P>(s->view, l);
+                else if (l.state == ST_DESC) desc_step<false, 8 * P>(s->view, l, &cn);
+                else if (l.state == ST_ENTER) enter_step<false>(s->view, l, &cn);
+                else if (l.state == ST_LEAF) tri_step<false>(s->view, l, &cn);
+            }
+        }
+        for (int k = 0; k < m; ++k) {                        // report like BatchPolicy: position in the parsed list, -1 = Nothing
+            const int t = L[k].cur.tri;
+            tri_out[base + k] = t < 0 ? -1 : ((uint32_t)t >= s->view.n_tris ? t : (int)f2u(s->tris[3 * (size_t)t + 2].z));
+            dist_out[base + k] = t < 0 ? 0.0f : L[k].cur.dist;
+        }
+        for (size_t c = (size_t)P * stride; c < region.size(); ++c) if (region[c] != 0xdeadbeefu) bad = 1;
+    }
+    return bad;
+}
+
 // One render.  The device runs 32 lanes per warp in lock step; lanes are independent, so here `n_lanes` software
 // lanes each run to completion, sharing one work queue like the device lanes share the atomic counter.
 // stats5 = rays, samples, primary_reused, branch_visits, tri_tests

@@ -37,6 +37,29 @@ def test_adversarial_rays(emu, oracle_scene):
     assert_same_hits(emu.intersect_batch(org, dirs), oracle_scene.intersect_batch(org, dirs), "adversarial")
 
 
+def test_interleaved_stack_layout(emu, oracle_scene, camera):
+    """The pool kernel keeps the stacks of a warp's 64 rays in one region, interleaved in 32-byte granules, with the
+    stride launch_pool derives from the tree height.  Host run of exactly that layout, 64 live rays stepped round-robin:
+    same hits as the oracle and nothing written behind the region."""
+    org, dirs = random_rays(6000, seed=11)
+    o2, d2 = O.make_rays(O.make_params(64, 48, 1), camera)
+    org = np.concatenate([org, o2]); dirs = np.concatenate([dirs, d2])
+    tri, dist, bad = emu.intersect_batch_interleaved(org, dirs)
+    ref = oracle_scene.intersect_batch(org, dirs)
+    assert bad == 0
+    assert np.array_equal(tri, ref[0]) and np.array_equal(dist.view(np.uint32), ref[1].view(np.uint32))
+    assert (tri >= 0).mean() > 0.3
+    # a deeper tree (triangle soup: height 15+, many both-children-hit branches -> deep stacks)
+    v9, mi, mats = scenes.triangle_soup(120000, seed=3)
+    osc, hs = build_pair(v9 * 40.0, mi, mats)
+    deep = Emu(hs)
+    org, dirs = random_rays(3000, seed=12, lo=-20, hi=20)
+    tri, dist, bad = deep.intersect_batch_interleaved(org, dirs)
+    ref = osc.intersect_batch(org, dirs)
+    assert bad == 0 and hs.stats()["height"] >= 15
+    assert np.array_equal(tri, ref[0]) and np.array_equal(dist.view(np.uint32), ref[1].view(np.uint32))
+
+
 @pytest.mark.parametrize("gen,n", [("cornell", 4000), ("soup", 30000), ("mesh", 20000)])
 def test_synthetic_scenes(gen, n):
     v9, mi, mats = {"cornell": scenes.cornell_box, "soup": scenes.triangle_soup, "mesh": scenes.subdivided_mesh}[gen](n)
