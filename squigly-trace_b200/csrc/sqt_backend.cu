@@ -278,8 +278,8 @@ struct PoolTune { int burst_t, burst_l, c_min; };
 #endif
 
 // 16 words = 64 B per ray in shared memory.  PF_MI holds `meta` while the ray descends / enters and `i` while it is in a
-// leaf; PF_FLAGS = state | safe << 8 | sgn << 16 | sp << 24.  (4 warps x 64 rays x 64 B + lists = 16.5 KB per CTA, so
-// 8 CTAs fit the 132 KB shared-memory carve-out and ~90 KB stay L1.)
+// leaf; PF_FLAGS = state | safe << 8 | sgn << 16 | sp << 24.  (4 warps x 64 rays x 64 B + lists = 16.5 KB per CTA:
+// the 9 CTAs per SM that 56 registers allow take 149 KB of shared memory and ~79 KB stay L1.)
 enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_MI, PF_CTRI, PF_CT, PF_CDIST, PF_FLAGS,
        PF_DFAC, PF_WORDS };
 // the integrator state of a slot (PathRay) is only touched by regeneration: 8 words per slot in global memory
