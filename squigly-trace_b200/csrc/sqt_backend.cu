@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(128, SQT_WL_MIN_BLOCKS) k_paths(SceneView sc, 
 // traversal step, a leaf entry, a triangle test or regeneration, picks the kind with the most waiting rays, gathers
 // up to 32 of them onto its lanes (rank by ballot, scatter slot ids through shared memory), runs a short burst of
 // that one kind of step with (nearly) all lanes active, and writes the rays back.  With one ray per lane at most
-// ~10 of 32 lanes share a step kind at any time (tools/sched_sim.py); regrouping rays lifts that limit.
+// ~10 of 32 lanes share a step kind at any time (tests/sched_sim.py); regrouping rays lifts that limit.
 #ifndef SQT_POOL_MIN_BLOCKS
 #define SQT_POOL_MIN_BLOCKS 9
 #endif
