@@ -46,8 +46,9 @@ enum {
 /* ---- flattened BIH (BIH.hs:26,37-43), nodes in any order with node 0 = root ------------------
  * Branch (BIHN axis lmax rmin) l r : a = index(l) | axis<<30 ,  b = index(r)             (axis X=0,Y=1,Z=2)
  * Leaf tris                         : a = first triangle in tris[] , b = count | 0x80000000   (lmax,rmin ignored)
- * Node indices must be < 2^30.  Child boxes are NOT stored: the library derives them exactly as
- * BIH.hs:130-141 does, by clipping the parent's box (plain copies of lmax/rmin, no arithmetic). */
+ * At most 2^28 - 1 nodes and 2^27 - 1 triangles.  Child boxes are NOT stored: the library derives them exactly as
+ * BIH.hs:130-141 does, by clipping the parent's box (plain copies of lmax/rmin, no arithmetic).  The `pad` word of
+ * a triangle is ignored on input (the device copy uses it). */
 typedef struct sqt_node {
     float lmax, rmin;
     uint32_t a, b;
@@ -143,6 +144,15 @@ const char *sqt_last_error(const sqt_ctx *ctx);        /* ctx may be NULL: error
 
 /* replaces the in-memory `Scene BIH` value handed to render (Main.hs:39,55-56) ------------- */
 int sqt_upload_scene(sqt_ctx *ctx, const sqt_scene_desc *scene);
+
+/* The same scene onto every context of a single-process group (ctxs[0..n) on n distinct devices): the tree is walked
+ * once and every staged chunk of triangles is sent to all devices.  What the Haskell host calls once per run. */
+int sqt_upload_scene_group(sqt_ctx **ctxs, int n, const sqt_scene_desc *scene);
+
+/* what the last sqt_upload_scene[_group] on this context moved and cost: bytes copied host -> device, wall time of the
+ * call, and the part of it the host spent walking the tree (the rest is copies + two device kernels).  Any pointer may
+ * be NULL. */
+int sqt_last_upload(const sqt_ctx *ctx, uint64_t *h2d_bytes, double *wall_ms, double *host_layout_ms);
 
 /* optional, after sqt_upload_scene: n = 0 removes the spheres again */
 int sqt_upload_spheres(sqt_ctx *ctx, const sqt_sphere *spheres, uint32_t n);

@@ -1,541 +1,24 @@
-// sqt_backend.cu -- sm_100a kernels and the C ABI (include/sqt.h) of the squigly-trace B200 backend.
+// sqt_backend.cu -- context, scene upload and the C ABI (include/sqt.h) of the squigly-trace B200 backend.
 //
-// Kernels
-//   k_intersect_batch  : one lane per ray, grid-stride; batched Scene.intersect (Geometry.hs:64 / BIH.hs:101)
-//   k_primary          : one lane per pixel; makeRay (Lib.hs:107-114) + closest hit, cached per pixel
-//   k_paths_pool       : the integrator: every warp owns a pool of 32*K rays in shared memory and regroups them by
-//                        the kind of step they need (default)
-//   k_paths            : the integrator with one ray per lane and warp-synchronous phases (SQT_POOL=0)
-//   k_accumulate       : adds a round's samples to the per-pixel sums in sample order (Lib.hs:88)
-//   k_raycast          : --cast mode (Lib.hs:141-151)
-//   k_tonemap          : mean + rgbFloatToPixelRGB (Lib.hs:88-104)
-//   k_fp32_peak, k_l2_read : roofline denominators measured on the device
-// Host side: context, scene upload (derives the 64-byte branch and 32-byte leaf records from the 16-byte boundary nodes),
-// NCCL group (dlopen'ed), CUDA-event timing of every launch.
+// The kernels live in sqt_kernels.cuh (per-ray logic in sqt_core.cuh / sqt_paths.cuh), the NCCL shim in sqt_nccl.hpp,
+// the host-side derivation of the device records in sqt_layout.hpp.  Every launch is bracketed by CUDA events on the
+// context's stream.
 //
 // There is no CPU fallback in this file: every entry point needs a compute-capability-10.x device.
 #include <cuda_runtime.h>
-#include <cooperative_groups.h>
-#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
-#include <type_traits>
 #include <vector>
 
 #include "../../include/sqt.h"
-#include "sqt_paths.cuh"
+#include "sqt_kernels.cuh"
 #include "sqt_layout.hpp"
-
-namespace cg = cooperative_groups;
-using namespace sqt;
-
-// =============================================================================== kernels
-struct DeviceStats {
-    unsigned long long rays, samples, primary_reused;
-    unsigned long long branch_visits, child_box_tests, tri_tests, leaves_culled;
-    unsigned long long mt_pass_a, mt_pass_u, mt_pass_v, mt_accept;
-    unsigned long long n_hit;           // length of the pixel list k_primary builds
-    unsigned long long work_next[256];  // dynamic work counters of the path kernels, one per round
-};
-
-__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    return v;
-}
-// every lane of the block must call this (full warps)
-__device__ __forceinline__ void flush_stats(DeviceStats *ds, const PathStats &st, const Counters &cn, bool count) {
-    unsigned long long r = warp_sum(st.rays), s = warp_sum(st.samples), p = warp_sum(st.primary_reused);
-    unsigned long long b = 0, c = 0, t = 0;
-    unsigned long long lc = 0, ga = 0, gu = 0, gv = 0, gt = 0;
-    if (count) {
-        b = warp_sum(cn.branch_visits); c = warp_sum(cn.child_box_tests); t = warp_sum(cn.tri_tests); lc = warp_sum(cn.leaves_culled);
-        ga = warp_sum(cn.mt_pass_a); gu = warp_sum(cn.mt_pass_u); gv = warp_sum(cn.mt_pass_v); gt = warp_sum(cn.mt_accept);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (r) atomicAdd(&ds->rays, r);
-        if (s) atomicAdd(&ds->samples, s);
-        if (p) atomicAdd(&ds->primary_reused, p);
-        if (count) { atomicAdd(&ds->branch_visits, b); atomicAdd(&ds->child_box_tests, c); atomicAdd(&ds->tri_tests, t); atomicAdd(&ds->leaves_culled, lc);
-            atomicAdd(&ds->mt_pass_a, ga); atomicAdd(&ds->mt_pass_u, gu); atomicAdd(&ds->mt_pass_v, gv); atomicAdd(&ds->mt_accept, gt); }
-    }
-}
-
-// Scheduling knobs of the warp-synchronous loop (runtime so that they can be tuned without rebuilding; they
-// change the order in which lanes get served, never a result):
-//   a_leave : leave the traversal phase once at most this many lanes still want a traversal step
-//   b_leave : leave the triangle phase once fewer than this many lanes still have triangles to test
-//             (0 = the warp-cooperative triangle phase below, which always runs to completion)
-//   c_min   : run the regeneration phase only when at least this many lanes are done (or nothing else can run)
-struct Tune { int a_leave, b_leave, c_min; };
-
-// Warp-cooperative triangle phase.  The lanes that wait in a leaf hold (first triangle, triangles left); their
-// remaining (ray, triangle) tests are laid out consecutively by an exclusive scan and executed 32 at a time, one
-// test per lane, whichever lane owns the ray: the owner of test p is found by a binary search over the scan
-// (shuffles), the ray comes from the owner by shuffle.  Accepted hits (about one test in seventy) are handed back
-// to the owner one after the other in test order, i.e. from the leaf's last triangle to its first, so every ray
-// sees exactly the sequence of min' applications of BIH.hs:105-109 (base-4.9 minimumBy = foldr1 min').
-// Moller-Trumbore is a pure function of (ray, triangle), so only the lane that evaluates it changes.
-template <bool COUNT>
-__device__ __forceinline__ void leaf_pairs(const SceneView &sc, TravLane &L, Counters *cn) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const bool in_leaf = L.state == ST_LEAF;
-    const int left = in_leaf ? L.i + 1 : 0;
-    const int cnt = left < 1024 ? left : 1024;            // a pathological leaf is worked off over several phases
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int start = incl - cnt;
-    const int total = __shfl_sync(FULL, incl, 31);
-    for (int base = 0; base < total; base += 32) {
-        const int pr = base + lane;
-        int own = 0;                                       // first lane whose inclusive scan exceeds pr
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            const int v = __shfl_sync(FULL, incl, own + s - 1);
-            if (v <= pr) own += s;
-        }
-        Ray r;
-        r.ox = __shfl_sync(FULL, L.r.ox, own); r.oy = __shfl_sync(FULL, L.r.oy, own); r.oz = __shfl_sync(FULL, L.r.oz, own);
-        r.dx = __shfl_sync(FULL, L.r.dx, own); r.dy = __shfl_sync(FULL, L.r.dy, own); r.dz = __shfl_sync(FULL, L.r.dz, own);
-        const uint32_t first = __shfl_sync(FULL, L.child, own);
-        const int oi = __shfl_sync(FULL, L.i, own), os = __shfl_sync(FULL, start, own);
-        const uint32_t idx = first + (uint32_t)(oi - (pr - os));
-        bool hit = false;
-        float t = 0.0f, dist = 0.0f;
-        if (pr < total) {
-            const TriData d = tri_load(sc, idx);
-            int stage;
-            hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
-            if (COUNT) { cn->mt_pass_a += stage >= 1; cn->mt_pass_u += stage >= 2; cn->mt_pass_v += stage >= 3; cn->mt_accept += stage >= 4; }
-        }
-        unsigned hm = __ballot_sync(FULL, hit);
-        while (hm != 0u) {                                 // rare: hand each accepted hit to its owner, in test order
-            const int src = __ffs(hm) - 1;
-            hm &= hm - 1u;
-            const int o_s = __shfl_sync(FULL, own, src);
-            const float t_s = __shfl_sync(FULL, t, src), d_s = __shfl_sync(FULL, dist, src);
-            const uint32_t i_s = __shfl_sync(FULL, idx, src);
-            if (lane == o_s && (L.cur.tri < 0 || !cmp_gt(d_s, L.cur.dist))) { L.cur.tri = (int)i_s; L.cur.t = t_s; L.cur.dist = d_s; }
-        }
-    }
-    if (in_leaf) {
-        L.i -= cnt;
-        if (L.i < 0) L.state = ST_RET;
-    }
-}
-
-// The persistent warp loop.  Every lane of the warp stays in it until all 32 have run out of work.  A round is
-// three phases, each a tight loop whose trip count is decided by a warp vote: regeneration (consume the finished
-// hit, shade, make the next ray), traversal steps (stack pops + one branch visit), triangle steps (one
-// Moller-Trumbore test).  The votes force the 32 lanes back together at every phase boundary; an ordinary
-// per-lane loop nest compiles to code where the lanes drift apart through the data-dependent traversal and
-// never reconverge (measured: 2.4 of 32 lanes active, profiles/r01_k_paths_v0_divergent.txt).
-template <class P, class = void> struct has_warp_regen : std::false_type {};
-template <class P> struct has_warp_regen<P, std::void_t<decltype(P::kWarpRegen)>> : std::true_type {};
-
-template <bool COUNT, class Policy>
-__device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Counters *cn, const Tune tn) {
-    const unsigned FULL = 0xffffffffu;
-    uint32_t stack[kStackWords];
-    TravLane L;
-    L.stack = stack;
-    L.state = ST_DONE; L.sp = 0; L.i = 0; L.child = 0u; L.meta = 0u; L.safe = true; L.sgn = 0u; L.dfac = 0.0f;
-    L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
-    L.dfx = L.dfy = L.dfz = 0.0f;
-    L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
-    for (;;) {
-        // ---- regeneration
-        const unsigned m_done = __ballot_sync(FULL, L.state == ST_DONE);
-        const unsigned m_busy = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET || L.state == ST_LEAF || L.state == ST_ENTER);
-        if (m_done != 0u && (__popc(m_done) >= tn.c_min || m_busy == 0u)) {
-            if constexpr (has_warp_regen<Policy>::value) pol.template regen_warp<COUNT>(sc, L, cn, L.state == ST_DONE);
-            else { if (L.state == ST_DONE) pol.template regen<COUNT>(sc, L, cn); }
-            __syncwarp(FULL);
-        } else if (m_busy == 0u) break;                       // every lane is ST_EXIT
-        // ---- traversal steps (stack pops + one branch visit) while more than a_leave lanes want one; then every
-        //      lane that found a leaf enters it (record fetch + conservative culling; culled lanes traverse on).
-        //      The few stragglers left over keep their state and continue next round.
-        for (;;) {
-            const unsigned mt = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET);
-            if (__popc(mt) > tn.a_leave) {
-                if (L.state == ST_RET) ret_step(sc, L);
-                if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
-                continue;
-            }
-            if (__any_sync(FULL, L.state == ST_ENTER)) {
-                if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, cn);
-                continue;
-            }
-            if (mt != 0u && !__any_sync(FULL, L.state == ST_LEAF)) {      // only stragglers are left and nobody has triangles
-                if (L.state == ST_RET) ret_step(sc, L);
-                if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
-                continue;
-            }
-            break;
-        }
-        // ---- triangle tests: all lanes share the tests of the lanes that wait in a leaf, or one test per lane and step
-        unsigned m = __ballot_sync(FULL, L.state == ST_LEAF);
-        if (tn.b_leave == 0) {
-            if (m != 0u) leaf_pairs<COUNT>(sc, L, cn);
-            continue;
-        }
-        while (m != 0u) {
-            if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, cn);
-            m = __ballot_sync(FULL, L.state == ST_LEAF);
-            if (__popc(m) < tn.b_leave) break;
-        }
-    }
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_intersect_batch(SceneView sc, const float *__restrict__ org,
-                                                         const float *__restrict__ dir, long long n,
-                                                         int *__restrict__ tri_out, float *__restrict__ dist_out,
-                                                         float *__restrict__ point_out, DeviceStats *ds, Tune tn) {
-    Counters cn = {};
-    PathStats st = {0, 0, 0};
-    BatchPolicy pol(org, dir, n, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, tri_out,
-                    dist_out, point_out, st);
-    warp_loop<COUNT>(sc, pol, &cn, tn);
-    flush_stats(ds, st, cn, COUNT);
-}
-
-struct DeviceAppend {
-    unsigned long long *counter;
-    int *list;
-    __device__ __forceinline__ void operator()(long long pixel) {
-        cg::coalesced_group g = cg::coalesced_threads();
-        unsigned long long base = 0;
-        if (g.thread_rank() == 0) base = atomicAdd(counter, (unsigned long long)g.size());
-        base = g.shfl(base, 0);
-        list[base + g.thread_rank()] = (int)pixel;
-    }
-};
-
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_primary(SceneView sc, RenderParams p, int2 *__restrict__ prim, int *__restrict__ pixel_list,
-                                                 DeviceStats *ds, Tune tn) {
-    Counters cn = {};
-    PathStats st = {0, 0, 0};
-    DeviceAppend app = {&ds->n_hit, pixel_list};
-    PrimaryPolicy<DeviceAppend> pol(p, prim, app, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x,
-                                    (long long)gridDim.x * blockDim.x, st);
-    warp_loop<COUNT>(sc, pol, &cn, tn);
-    flush_stats(ds, st, cn, COUNT);
-}
-
-struct DeviceFetch {
-    unsigned long long *counter;
-    long long n;
-    __device__ __forceinline__ long long operator()() {
-        // warp-aggregated claim: one atomic per group of lanes that need work at the same time
-        cg::coalesced_group g = cg::coalesced_threads();
-        unsigned long long base = 0;
-        if (g.thread_rank() == 0) base = atomicAdd(counter, (unsigned long long)g.size());
-        base = g.shfl(base, 0);
-        const long long w = (long long)(base + g.thread_rank());
-        return w < n ? w : -1;
-    }
-};
-
-#ifndef SQT_WL_MIN_BLOCKS
-#define SQT_WL_MIN_BLOCKS 6
-#endif
-// One round of samples (sqt_paths.cuh): persistent lanes pull (pixel, sample) items from the round's counter.
-template <bool COUNT>
-__global__ void __launch_bounds__(128, SQT_WL_MIN_BLOCKS) k_paths(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, Tune tn) {
-    Counters cn = {};
-    PathStats st = {0, 0, 0};
-    if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
-    DeviceFetch fetch = {&ds->work_next[round], rd.n_slots << rd.log2_s};
-    uint16_t pm[SQT_MAX_DEPTH];
-    PathPolicy<DeviceFetch> pol(p, rd, fetch, st, pm);
-    warp_loop<COUNT>(sc, pol, &cn, tn);
-    flush_stats(ds, st, cn, COUNT);
-}
-
-// ------------------------------------------------------------------------------ ray pools
-// k_paths_pool: the same per-ray logic as k_paths, scheduled differently.  Every warp owns a POOL of P = 32*K rays
-// whose state lives in shared memory (structure of arrays, 16 words per ray; traversal stacks, per-path material
-// lists and the integrator state of a slot in global memory, one region per pool slot).  Each round the warp counts how many of its rays wait for a
-// traversal step, a leaf entry, a triangle test or regeneration, picks the kind with the most waiting rays, gathers
-// up to 32 of them onto its lanes (rank by ballot, scatter slot ids through shared memory), runs a short burst of
-// that one kind of step with (nearly) all lanes active, and writes the rays back.  With one ray per lane at most
-// ~10 of 32 lanes share a step kind at any time (tests/sched_sim.py); regrouping rays lifts that limit.
-#ifndef SQT_POOL_MIN_BLOCKS
-#define SQT_POOL_MIN_BLOCKS 9
-#endif
-struct PoolTune { int burst_t, burst_l, c_min; };
-#ifndef SQT_POOL_TRI_UNROLL
-#define SQT_POOL_TRI_UNROLL 2
-#endif
-
-// 16 words = 64 B per ray in shared memory.  PF_MI holds `meta` while the ray descends / enters and `i` while it is in a
-// leaf; PF_FLAGS = state | safe << 8 | sgn << 16 | sp << 24.  (4 warps x 64 rays x 64 B + lists = 16.5 KB per CTA:
-// the 9 CTAs per SM that 56 registers allow take 149 KB of shared memory and ~79 KB stay L1.)
-enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_MI, PF_CTRI, PF_CT, PF_CDIST, PF_FLAGS,
-       PF_DFAC, PF_WORDS };
-// the integrator state of a slot (PathRay) is only touched by regeneration: 8 words per slot in global memory
-
-template <bool COUNT, int K>
-__global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, PoolTune tn,
-                                                    uint32_t *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath, int stack_stride, int pm_stride) {
-    extern __shared__ uint32_t pool_smem[];
-    constexpr int P = 32 * K;
-    const unsigned FULL = 0xffffffffu;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *pool = pool_smem + warp * (P * PF_WORDS + 32);
-    uint32_t *sel = pool + P * PF_WORDS;
-    const int gslot0 = (int)((blockIdx.x * (blockDim.x >> 5) + warp) * P);     // < 2^31: at most a few hundred thousand pool slots exist
-#define PW(f, slot) pool[(f) * P + (slot)]
-    Counters cn = {};
-    PathStats st = {0, 0, 0};
-    if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
-    DeviceFetch fetch = {&ds->work_next[round], rd.n_slots << rd.log2_s};
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int slot = lane + 32 * k;
-        PW(PF_FLAGS, slot) = (uint32_t)ST_DONE;
-        PW(PF_CTRI, slot) = 0xffffffffu;
-        gpath[2 * (gslot0 + slot)] = make_uint4(0u, 0u, 0u, 0u);
-        gpath[2 * (gslot0 + slot) + 1] = make_uint4(0u, 0u, 0u, 0u);      // saved_j = -1 (stored +1), any_emit = in_flight = false
-    }
-    __syncwarp(FULL);
-    const unsigned lt_mask = (1u << lane) - 1u;
-    for (;;) {
-        // ---- census of the pool: every lane classifies its K slots (kind 0 = traversal, 1 = leaf entry, 2 = triangle,
-        //      3 = regeneration, 7 = exited), packs one count byte per kind and the warp adds the packed words (REDUX)
-        int kk[K];
-        unsigned packed = 0u;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const unsigned sst = PW(PF_FLAGS, lane + 32 * k) & 0xffu;
-            // ST_DONE 0 -> 3, ST_DESC 1 -> 0, ST_LEAF 2 -> 2, ST_RET 3 -> 0, ST_EXIT 4 -> 7, ST_ENTER 5 -> 1
-            const int kd = (int)(0x170203u >> (4u * sst)) & 7;
-            kk[k] = kd;
-            packed += kd == 7 ? 0u : (1u << (8 * kd));
-        }
-        packed = __reduce_add_sync(FULL, packed);
-        if (packed == 0u) break;                                            // every slot is ST_EXIT
-        const int n_t = (int)(packed & 0xffu), n_e = (int)((packed >> 8) & 0xffu), n_l = (int)((packed >> 16) & 0xffu), n_r = (int)(packed >> 24);
-        // ---- pick the kind of step with the most waiting rays (regeneration only in batches)
-        const int c_r = (n_r >= tn.c_min || (packed & 0x00ffffffu) == 0u) ? n_r : 0;
-        int kind = 2, best = n_l;
-        if (n_t > best) { kind = 0; best = n_t; }
-        if (n_e > best) { kind = 1; best = n_e; }
-        if (c_r > best) { kind = 3; best = c_r; }
-        // ---- gather up to 32 rays of that kind onto the lanes
-        int base = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const bool mine = kk[k] == kind;
-            const unsigned b = __ballot_sync(FULL, mine);
-            const int rank = base + __popc(b & lt_mask);
-            if (mine && rank < 32) sel[rank] = (uint32_t)(lane + 32 * k);
-            base += __popc(b);
-        }
-        __syncwarp(FULL);
-        const int n_sel = base < 32 ? base : 32;
-        const bool act = lane < n_sel;
-        const int slot = act ? (int)sel[lane] : 0;
-        TravLane L;
-        L.stack = nullptr;                                                  // only traversal steps touch the stack
-        if (kind == 2) {
-            // ---- triangle tests
-            if (act) {
-                L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
-                L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
-                L.child = PW(PF_CHILD, slot); L.i = (int)PW(PF_MI, slot);
-                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
-                L.state = ST_LEAF;
-            } else L.state = ST_EXIT;
-            for (int b = 0; b < tn.burst_l; b += SQT_POOL_TRI_UNROLL) {  // several tests per vote
-#pragma unroll
-                for (int u = 0; u < SQT_POOL_TRI_UNROLL; ++u)
-                    if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, &cn);
-                if (!__any_sync(FULL, L.state == ST_LEAF)) break;
-            }
-            if (act) {
-                PW(PF_MI, slot) = (uint32_t)L.i;
-                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
-                if (L.state != ST_LEAF) PW(PF_FLAGS, slot) = (PW(PF_FLAGS, slot) & ~0xffu) | (uint32_t)L.state;
-            }
-        } else if (kind == 0) {
-            // ---- traversal steps: stack pops + branch visits
-            uint32_t fl = 0u;
-            L.stack = gstack + (size_t)gslot0 * (size_t)stack_stride + 8 * slot;     // the warp's P stacks, interleaved in 32-byte granules
-            if (act) {
-                L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
-                L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
-                L.dfx = u2f(PW(PF_DFX, slot)); L.dfy = u2f(PW(PF_DFY, slot)); L.dfz = u2f(PW(PF_DFZ, slot));
-                L.child = PW(PF_CHILD, slot); L.meta = PW(PF_MI, slot);
-                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
-                fl = PW(PF_FLAGS, slot);
-                L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
-            } else L.state = ST_EXIT;
-            for (int b = 0; b < tn.burst_t; ++b) {                        // (two steps per vote: the second copy of the step costs more than the vote, -16 %)
-                if (L.state == ST_RET) ret_step<8 * P>(sc, L);
-                if (L.state == ST_DESC) desc_step<COUNT, 8 * P>(sc, L, &cn);
-                if (!__any_sync(FULL, L.state == ST_DESC || L.state == ST_RET)) break;
-            }
-            if (act) {
-                PW(PF_CHILD, slot) = L.child; PW(PF_MI, slot) = L.meta;
-                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
-                PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
-            }
-        } else if (kind == 1) {
-            // ---- leaf entry: record fetch + conservative culling
-            if (act) {
-                L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
-                L.dfx = u2f(PW(PF_DFX, slot)); L.dfy = u2f(PW(PF_DFY, slot)); L.dfz = u2f(PW(PF_DFZ, slot));
-                L.dfac = u2f(PW(PF_DFAC, slot));
-                L.child = PW(PF_CHILD, slot); L.meta = PW(PF_MI, slot);
-                const uint32_t fl = PW(PF_FLAGS, slot);
-                L.safe = ((fl >> 8) & 1u) != 0u;
-                L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f; L.i = 0;
-                L.state = ST_ENTER;
-                enter_step<COUNT>(sc, L, &cn);
-                PW(PF_CHILD, slot) = L.child; PW(PF_MI, slot) = (uint32_t)L.i; PW(PF_CTRI, slot) = (uint32_t)L.cur.tri;
-                PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)L.state;
-            }
-        } else {
-            // ---- regeneration: consume the finished hit, shade, start the next ray (or the next sample); staged, all
-            //      gathered lanes together (path_regen_warp)
-            PathRay q;
-            path_ray_init(q);
-            uint4 *gp = gpath + 2 * (gslot0 + slot);
-            L.dfx = L.dfy = L.dfz = 0.0f; L.dfac = 0.0f; L.child = 0u; L.meta = 0u; L.i = 0; L.sp = 0; L.safe = true; L.sgn = 0u;
-            L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
-            L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
-            L.state = ST_EXIT;
-            if (act) {
-                L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
-                L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
-                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
-                L.state = ST_DONE;
-                const uint4 g0 = gp[0], g1 = gp[1];
-                const uint32_t pf = g1.y;
-                q.sidx = g0.x; q.j = (int)g0.y;
-                q.stream = (unsigned long long)g0.z | ((unsigned long long)g0.w << 32);
-                q.saved_r = u2f(g1.x); q.saved_j = (int)(pf & 0xffffu) - 1;
-                q.any_emit = ((pf >> 16) & 1u) != 0u; q.in_flight = ((pf >> 17) & 1u) != 0u;
-            }
-            path_regen_warp<COUNT>(sc, p, rd, fetch, st, q, gpm + (size_t)(gslot0 + slot) * (size_t)pm_stride, L, &cn, act);
-            if (act) {
-                PW(PF_OX, slot) = f2u(L.r.ox); PW(PF_OY, slot) = f2u(L.r.oy); PW(PF_OZ, slot) = f2u(L.r.oz);
-                PW(PF_DX, slot) = f2u(L.r.dx); PW(PF_DY, slot) = f2u(L.r.dy); PW(PF_DZ, slot) = f2u(L.r.dz);
-                PW(PF_DFX, slot) = f2u(L.dfx); PW(PF_DFY, slot) = f2u(L.dfy); PW(PF_DFZ, slot) = f2u(L.dfz);
-                PW(PF_CHILD, slot) = L.child; PW(PF_MI, slot) = L.state == ST_LEAF ? (uint32_t)L.i : L.meta;
-                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
-                PW(PF_DFAC, slot) = f2u(L.dfac);
-                PW(PF_FLAGS, slot) = (uint32_t)L.state | (L.safe ? 0x100u : 0u) | (L.sgn << 16) | ((uint32_t)L.sp << 24);
-                gp[0] = make_uint4(q.sidx, (uint32_t)q.j, (uint32_t)q.stream, (uint32_t)(q.stream >> 32));
-                gp[1] = make_uint4(f2u(q.saved_r), (uint32_t)(q.saved_j + 1) | (q.any_emit ? 0x10000u : 0u) | (q.in_flight ? 0x20000u : 0u), 0u, 0u);
-            }
-        }
-        __syncwarp(FULL);
-    }
-#undef PW
-    flush_stats(ds, st, cn, COUNT);
-}
-
-// sum the round's samples into the per-pixel running sums, in sample order (Lib.hs:88)
-__global__ void __launch_bounds__(256) k_accumulate(RenderParams p, RoundInfo rd, float *__restrict__ accum, const DeviceStats *ds) {
-    if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < rd.n_slots; slot += stride)
-        accumulate_slot(p, rd, slot, accum);
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_raycast(SceneView sc, RenderParams p, float *__restrict__ accum, DeviceStats *ds, Tune tn) {
-    Counters cn = {};
-    PathStats st = {0, 0, 0};
-    CastPolicy pol(p, accum, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, st);
-    warp_loop<COUNT>(sc, pol, &cn, tn);
-    flush_stats(ds, st, cn, COUNT);
-}
-
-// avg = (1 / fromIntegral sampleCount) *^ sum outcomes ; rgbFloatToPixelRGB avg   (Lib.hs:88-89)
-__global__ void __launch_bounds__(256) k_tonemap(const float *__restrict__ accum, long long npix, float inv_spp,
-                                                 uint8_t *__restrict__ rgb8) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
-    uint8_t o[3];
-    tone_map(XMUL(inv_spp, accum[3 * i]), XMUL(inv_spp, accum[3 * i + 1]), XMUL(inv_spp, accum[3 * i + 2]), o);
-    rgb8[3 * i] = o[0]; rgb8[3 * i + 1] = o[1]; rgb8[3 * i + 2] = o[2];
-}
-
-// Non-fused FP32 issue rate: 16 independent chains per lane, alternating FMUL / FADD (the op mix of the
-// bit-exact intersection path, where FMA contraction is forbidden).
-__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float a, float b) {
-    float x[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) { x[i] = __fmul_rn(x[i], a); x[i + 1] = __fadd_rn(x[i + 1], b); }
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) { x[i] = __fadd_rn(x[i], b); x[i + 1] = __fmul_rn(x[i + 1], a); }
-    }
-    float s = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s += x[i];
-    if (s == 123.456f) out[0] = s;      // keep the chains alive
-}
-
-// L2-resident 128-bit read bandwidth: every block sweeps the same `n4`-element buffer `reps` times.
-__global__ void __launch_bounds__(256) k_l2_read(const float4 *__restrict__ buf, long long n4, int reps, float *out) {
-    float s = 0.0f;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (int r = 0; r < reps; ++r)
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-            float4 v;
-            asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(buf + i));
-            s += v.x + v.y + v.z + v.w;
-        }
-    if (s == 123.456f) out[0] = s;
-}
-
-// ============================================================================== NCCL (dlopen)
-typedef struct ncclComm *ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-typedef int ncclResult_t;
-struct NcclApi {
-    void *lib = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*Reduce)(const void *, void *, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    const char *(*GetErrorString)(ncclResult_t) = nullptr;
-    std::string err;
-};
-static NcclApi *nccl_api() {
-    static NcclApi api;
-    static bool tried = false;
-    if (tried) return &api;
-    tried = true;
-    const char *names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
-    for (const char *n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
-    if (!api.lib) { api.err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return &api; }
-#define SQT_SYM(field, name) *(void **)(&api.field) = dlsym(api.lib, name); if (!api.field) { api.err = "NCCL symbol missing: " name; api.lib = nullptr; return &api; }
-    SQT_SYM(GetUniqueId, "ncclGetUniqueId") SQT_SYM(CommInitRank, "ncclCommInitRank") SQT_SYM(CommInitAll, "ncclCommInitAll")
-    SQT_SYM(CommDestroy, "ncclCommDestroy") SQT_SYM(Reduce, "ncclReduce") SQT_SYM(GroupStart, "ncclGroupStart")
-    SQT_SYM(GroupEnd, "ncclGroupEnd") SQT_SYM(GetErrorString, "ncclGetErrorString")
-#undef SQT_SYM
-    return &api;
-}
-static const int kNcclFloat32 = 7, kNcclSum = 0;
+#include "sqt_nccl.hpp"
 
 // ============================================================================== context
 struct sqt_ctx {
@@ -547,7 +30,11 @@ struct sqt_ctx {
     // scene
     bool has_scene = false;
     SceneView sc = {};
-    float4 *d_nodes = nullptr, *d_tris = nullptr, *d_mats = nullptr, *d_leaves = nullptr, *d_spheres = nullptr;
+    float4 *d_nodes = nullptr, *d_boxes = nullptr, *d_tris = nullptr, *d_mats = nullptr, *d_leaves = nullptr, *d_spheres = nullptr;
+    uint2 *d_ranges = nullptr;          // (first, count) per leaf, input of k_leaf_records
+    uint32_t *d_flag = nullptr;         // material check result
+    size_t cap_branches = 0, cap_leaves = 0, cap_tris = 0, cap_mats = 0;     // allocation sizes (records), reused across uploads
+    uint64_t upload_bytes = 0; double upload_ms = 0, upload_layout_ms = 0;   // last sqt_upload_scene
     int leaf_cull = 1;
     int terminate_on_black_ok = 0;
     uint32_t tree_height = 0;
@@ -571,9 +58,10 @@ struct sqt_ctx {
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
     Tune tune = {12, 0, 12};
     int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
-    PoolTune pool_tune = {4, 16, 16};
+    PoolTune pool_tune = {4, 6, 16};
     int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1
-    uint32_t *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0;
+    float4 *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0, cap_stack_entries = 0;
+    bool comm_broken = false;           // the communicator was aborted after a rank failed
     // group
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -593,8 +81,27 @@ extern "C" int sqt_abi_version(void) { return SQT_ABI_VERSION; }
 
 extern "C" const char *sqt_last_error(const sqt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Environment knobs (development only; they change scheduling, never a result).  Malformed values are ignored and every
+// value is clamped to a range in which the persistent kernels are guaranteed to make progress.
+static void read_env_tuning(sqt_ctx *c) {
+    if (const char *t = getenv("SQT_POOL")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 4) c->pool_k = (int)k; }
+    if (const char *t = getenv("SQT_POOL_BLOCKS")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 32) c->pool_blocks = (int)k; }
+    if (const char *t = getenv("SQT_POOL_TUNE")) {       // "burst_t,t_leave,c_min"
+        int a, b, cm;
+        if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->pool_tune = {clampi(a, 1, 64), clampi(b, 0, 31), clampi(cm, 1, 32)};
+    }
+    if (const char *t = getenv("SQT_SBUF_MB")) { char *e = nullptr; long long mb = strtoll(t, &e, 10); if (e != t && mb > 0 && mb < (1ll << 20)) c->sbuf_budget = mb << 20; }
+    if (const char *t = getenv("SQT_TUNE")) {            // "a_leave,b_leave,c_min"
+        int a, b, cm;
+        if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->tune = {clampi(a, 0, 31), clampi(b, 0, 32), clampi(cm, 1, 32)};
+    }
+}
+
+extern "C" int sqt_destroy(sqt_ctx *c);
+
 extern "C" int sqt_create(int device, sqt_ctx **out) {
-    sqt_ctx *ctx = nullptr;      // for CU(): errors before the context exists go to the thread-local slot
     if (!out) return fail(nullptr, SQT_E_INVALID, "sqt_create: out is NULL");
     *out = nullptr;
     int n = 0;
@@ -603,47 +110,46 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
         return fail(nullptr, SQT_E_NO_DEVICE, "no CUDA device (%s); this backend has no CPU fallback", cudaGetErrorString(e));
     if (device < 0 || device >= n) return fail(nullptr, SQT_E_INVALID, "device %d out of range (have %d)", device, n);
     cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, SQT_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
     if (prop.major != 10)
         return fail(nullptr, SQT_E_NO_DEVICE, "device %d (%s) is compute capability %d.%d; this library is built for sm_100a only",
                     device, prop.name, prop.major, prop.minor);
-    CU(cudaSetDevice(device));
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, SQT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     sqt_ctx *c = new sqt_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount; c->cc_major = prop.major; c->cc_minor = prop.minor;
     snprintf(c->name, sizeof c->name, "%s", prop.name);
-    ctx = c;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
-    CU(cudaMalloc(&c->d_stats, sizeof(DeviceStats)));
-    CU(cudaMallocHost(&c->h_stats, sizeof(DeviceStats)));
-    if (const char *t = getenv("SQT_POOL")) { int k = atoi(t); if (k >= 0 && k <= 4) c->pool_k = k; }
-    if (const char *t = getenv("SQT_POOL_BLOCKS")) c->pool_blocks = atoi(t);
-    if (const char *t = getenv("SQT_POOL_TUNE")) {
-        int a, b, cm;
-        if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->pool_tune = {a, b, cm};
-    }
-    if (const char *t = getenv("SQT_SBUF_MB")) { long long mb = atoll(t); if (mb > 0) c->sbuf_budget = mb << 20; }
-    if (const char *t = getenv("SQT_TUNE")) {        // "a_leave,b_leave,c_min" -- scheduling knobs only, results do not depend on them
-        int a, b, cm;
-        if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->tune = {a, b, cm};
-    }
+    auto init = [&]() -> int {
+        sqt_ctx *ctx = c;
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
+        CU(cudaMalloc(&c->d_stats, sizeof(DeviceStats)));
+        CU(cudaMalloc(&c->d_flag, 2 * sizeof(uint32_t)));
+        CU(cudaMallocHost(&c->h_stats, sizeof(DeviceStats)));
+        return SQT_OK;
+    };
+    const int rc = init();
+    if (rc) { g_create_err = c->err; sqt_destroy(c); return rc; }        // no half-built context is leaked
+    read_env_tuning(c);
     *out = c;
     return SQT_OK;
 }
 
 static void free_scene(sqt_ctx *c) {
-    cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_mats); cudaFree(c->d_leaves); cudaFree(c->d_spheres);
-    c->d_nodes = c->d_tris = c->d_mats = c->d_leaves = c->d_spheres = nullptr; c->has_scene = false;
+    cudaFree(c->d_nodes); cudaFree(c->d_boxes); cudaFree(c->d_tris); cudaFree(c->d_mats); cudaFree(c->d_leaves); cudaFree(c->d_spheres); cudaFree(c->d_ranges);
+    c->d_nodes = c->d_boxes = c->d_tris = c->d_mats = c->d_leaves = c->d_spheres = nullptr; c->d_ranges = nullptr; c->has_scene = false;
+    c->cap_branches = c->cap_leaves = c->cap_tris = c->cap_mats = 0;
 }
 
 extern "C" int sqt_destroy(sqt_ctx *c) {
     if (!c) return SQT_OK;
     cudaSetDevice(c->device);
-    if (c->comm && nccl_api()->lib) nccl_api()->CommDestroy(c->comm);
+    if (c->comm && nccl_api()->lib && !c->comm_broken) nccl_api()->CommDestroy(c->comm);
     free_scene(c);
-    cudaFree(c->d_prim); cudaFree(c->d_accum); cudaFree(c->d_rgb8); cudaFree(c->d_stats); cudaFree(c->d_pixel_list); cudaFree(c->d_sbuf); cudaFree(c->d_gstack); cudaFree(c->d_gpm); cudaFree(c->d_gpath);
+    cudaFree(c->d_prim); cudaFree(c->d_accum); cudaFree(c->d_rgb8); cudaFree(c->d_stats); cudaFree(c->d_flag); cudaFree(c->d_pixel_list); cudaFree(c->d_sbuf); cudaFree(c->d_gstack); cudaFree(c->d_gpm); cudaFree(c->d_gpath);
     cudaFree(c->d_org); cudaFree(c->d_dir); cudaFree(c->d_dist); cudaFree(c->d_point); cudaFree(c->d_tri);
-    cudaFreeHost(c->h_stats); cudaFreeHost(c->h_rgb8); cudaFreeHost(c->h_accum);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->h_rgb8) cudaFreeHost(c->h_rgb8);
+    if (c->h_accum) cudaFreeHost(c->h_accum);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -660,38 +166,164 @@ extern "C" int sqt_device_info(sqt_ctx *c, int *sm_count, int *cc_major, int *cc
 }
 
 // ------------------------------------------------------------------------------ scene upload
-// Walks the boundary tree once (iteratively), validating it and deriving for every Branch the box
-// intersectBIH' would receive for it: the root gets `bounds`, a left child gets its parent's box with
-// hi[axis] := lmax, a right child the parent's box with lo[axis] := rmin (BIH.hs:130-141).
-extern "C" int sqt_upload_scene(sqt_ctx *ctx, const sqt_scene_desc *s) {
-    if (!ctx || !s) return SQT_E_INVALID;
-    CU(cudaSetDevice(ctx->device));
+// Host: one iterative walk over the boundary tree (sqt_layout.hpp) validates it and derives the 16-byte device nodes and
+// the clipped boxes (BIH.hs:130-141; plane values are copied, never computed).  Meanwhile a helper thread streams the
+// triangle array -- the bulk of a large scene -- to every context of the call through two pinned staging buffers.
+// Device: k_leaf_records derives the leaf records from the triangles, k_check_materials validates the material indices.
+// Device allocations are kept and reused while the new scene fits them.
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static int ensure_scene_capacity(sqt_ctx *ctx, size_t n_br, size_t n_lf, size_t n_tris, size_t n_mats) {
+    if (n_br > ctx->cap_branches) {
+        cudaFree(ctx->d_nodes); cudaFree(ctx->d_boxes); ctx->d_nodes = ctx->d_boxes = nullptr; ctx->cap_branches = 0;
+        CU(cudaMalloc(&ctx->d_nodes, n_br * sizeof(float4))); CU(cudaMalloc(&ctx->d_boxes, 2 * n_br * sizeof(float4)));
+        ctx->cap_branches = n_br;
+    }
+    if (n_lf > ctx->cap_leaves) {
+        cudaFree(ctx->d_leaves); cudaFree(ctx->d_ranges); ctx->d_leaves = nullptr; ctx->d_ranges = nullptr; ctx->cap_leaves = 0;
+        CU(cudaMalloc(&ctx->d_leaves, 2 * n_lf * sizeof(float4))); CU(cudaMalloc(&ctx->d_ranges, n_lf * sizeof(uint2)));
+        ctx->cap_leaves = n_lf;
+    }
+    if (n_tris > ctx->cap_tris) {
+        cudaFree(ctx->d_tris); ctx->d_tris = nullptr; ctx->cap_tris = 0;
+        CU(cudaMalloc(&ctx->d_tris, n_tris * 48));
+        ctx->cap_tris = n_tris;
+    }
+    if (n_mats > ctx->cap_mats) {
+        cudaFree(ctx->d_mats); ctx->d_mats = nullptr; ctx->cap_mats = 0;
+        CU(cudaMalloc(&ctx->d_mats, 3 * n_mats * sizeof(float4)));
+        ctx->cap_mats = n_mats;
+    }
+    return SQT_OK;
+}
+
+// triangles -> every context, chunk by chunk through two pinned buffers (runs on a helper thread)
+static void stream_tris(sqt_ctx **ctxs, int n, const sqt_tri *tris, size_t n_tris, std::atomic<int> *status, std::string *err) {
+    const size_t CH = (size_t)32 << 20, bytes = n_tris * 48;
+    void *pin[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> done(2 * (size_t)n);
+    auto bail = [&](cudaError_t e, const char *what) { *err = std::string(what) + ": " + cudaGetErrorString(e); status->store(SQT_E_CUDA); };
+    cudaError_t e = cudaSuccess;
+    bool have_ev = false;
+    do {
+        if (bytes == 0) break;
+        const size_t buf = bytes < CH ? bytes : CH;
+        if ((e = cudaSetDevice(ctxs[0]->device)) != cudaSuccess) { bail(e, "cudaSetDevice"); break; }
+        if ((e = cudaMallocHost(&pin[0], buf)) != cudaSuccess || (bytes > CH && (e = cudaMallocHost(&pin[1], buf)) != cudaSuccess)) { bail(e, "cudaMallocHost (staging)"); break; }
+        for (int g = 0; g < n && e == cudaSuccess; ++g) { cudaSetDevice(ctxs[g]->device); for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&done[2 * g + b], cudaEventDisableTiming); }
+        if (e != cudaSuccess) { bail(e, "cudaEventCreate"); break; }
+        have_ev = true;
+        size_t off = 0;
+        for (int it = 0; off < bytes; ++it) {
+            const int b = it & 1;
+            const size_t len = bytes - off < CH ? bytes - off : CH;
+            if (it >= 2) for (int g = 0; g < n; ++g) { cudaSetDevice(ctxs[g]->device); if ((e = cudaEventSynchronize(done[2 * g + b])) != cudaSuccess) break; }
+            if (e != cudaSuccess) { bail(e, "cudaEventSynchronize"); break; }
+            memcpy(pin[b], (const char *)tris + off, len);
+            for (int g = 0; g < n; ++g) {
+                cudaSetDevice(ctxs[g]->device);
+                if ((e = cudaMemcpyAsync((char *)ctxs[g]->d_tris + off, pin[b], len, cudaMemcpyHostToDevice, ctxs[g]->stream)) != cudaSuccess) break;
+                if ((e = cudaEventRecord(done[2 * g + b], ctxs[g]->stream)) != cudaSuccess) break;
+            }
+            if (e != cudaSuccess) { bail(e, "cudaMemcpyAsync (triangles)"); break; }
+            off += len;
+        }
+        for (int g = 0; g < n; ++g) { cudaSetDevice(ctxs[g]->device); cudaStreamSynchronize(ctxs[g]->stream); }
+    } while (false);
+    if (have_ev) for (int g = 0; g < n; ++g) { cudaSetDevice(ctxs[g]->device); for (int b = 0; b < 2; ++b) cudaEventDestroy(done[2 * g + b]); }
+    for (void *p : pin) if (p) cudaFreeHost(p);
+}
+
+static int upload_scene_to(sqt_ctx **ctxs, int n, const sqt_scene_desc *s) {
+    sqt_ctx *ctx = ctxs[0];
+    const double t0 = now_ms();
+    if (!s->nodes || s->n_nodes == 0) return fail(ctx, SQT_E_INVALID, "scene has no BIH nodes");
+    if (s->n_tris && !s->tris) return fail(ctx, SQT_E_INVALID, "tris is NULL");
+    if (s->n_tris >= (1u << 27) || s->n_nodes >= (1u << 28)) return fail(ctx, SQT_E_UNSUPPORTED, "scene too large for the 27/28-bit indices");
+    uint32_t n_br = 0, n_lf = 0;
+    for (uint32_t i = 0; i < s->n_nodes; ++i) { if (s->nodes[i].b & SQT_NODE_LEAF) ++n_lf; else ++n_br; }
+    for (int g = 0; g < n; ++g) {
+        sqt_ctx *c = ctxs[g];
+        cudaSetDevice(c->device);
+        c->has_scene = false;
+        const int rc = ensure_scene_capacity(c, n_br ? n_br : 1, n_lf ? n_lf : 1, s->n_tris ? s->n_tris : 1, s->n_mats ? s->n_mats : 1);
+        if (rc) { if (g) ctx->err = c->err; return rc; }
+    }
+    // the triangles start to flow while the host walks the tree
+    std::atomic<int> tri_status{0};
+    std::string tri_err;
+    std::thread streamer(stream_tris, ctxs, n, s->tris, (size_t)s->n_tris, &tri_status, &tri_err);
     DeviceLayout lay;
     std::string lerr;
-    const int lrc = build_device_layout(*s, lay, lerr);
+    const int lrc = build_device_layout(*s, lay, lerr, /*check_materials=*/false);
+    const double t1 = now_ms();
+    streamer.join();
     if (lrc) return fail(ctx, lrc, "%s", lerr.c_str());
-    std::vector<float4> &dn = lay.nodes;
-    std::vector<float4> &dm = lay.mats;
-    const uint32_t n_br = lay.n_branches, height = lay.height;
-    const int tob = lay.terminate_on_black_ok;
+    if (tri_status.load()) return fail(ctx, tri_status.load(), "%s", tri_err.c_str());
+    std::vector<uint2> ranges(lay.leaf_first.size());
+    for (size_t k = 0; k < ranges.size(); ++k) ranges[k] = make_uint2(lay.leaf_first[k], lay.leaf_count[k]);
+    const uint32_t n_leaves = n_lf;
+    for (int g = 0; g < n; ++g) {
+        sqt_ctx *c = ctxs[g];
+        sqt_ctx *ctx = c;       // CU() reports into this context
+        CU(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        const uint32_t init_flag[2] = {0xffffffffu, 0u};
+        CU(cudaMemcpyAsync(c->d_flag, init_flag, sizeof init_flag, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->d_nodes, lay.nodes.data(), lay.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->d_boxes, lay.boxes.data(), lay.boxes.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->d_mats, lay.mats.data(), lay.mats.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->d_ranges, ranges.data(), ranges.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+        if (n_leaves) {
+            k_leaf_records<<<(n_leaves + 255) / 256, 256, 0, st>>>(c->d_tris, c->d_ranges, n_leaves, c->d_leaves);
+            CU(cudaGetLastError());
+        }
+        if (s->n_tris) {
+            k_check_materials<<<(s->n_tris + 255) / 256, 256, 0, st>>>(c->d_tris, s->n_tris, s->n_mats, c->d_flag);
+            CU(cudaGetLastError());
+        }
+    }
+    for (int g = 0; g < n; ++g) {
+        sqt_ctx *c = ctxs[g];
+        sqt_ctx *ctx = c;
+        CU(cudaSetDevice(c->device));
+        uint32_t flag[2] = {0, 0};
+        CU(cudaMemcpyAsync(flag, c->d_flag, sizeof flag, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (flag[0] != 0xffffffffu) return fail(ctxs[0], SQT_E_INVALID, "triangle %u: material %u out of range", flag[0], s->tris[flag[0]].material);
+        SceneView v = {};
+        v.nodes = c->d_nodes; v.boxes = c->d_boxes; v.tris = c->d_tris; v.mats = c->d_mats; v.leaves = c->d_leaves;
+        v.leaf_cull = (uint32_t)c->leaf_cull;
+        for (int k = 0; k < 3; ++k) { v.root_lo[k] = s->root_bounds[k]; v.root_hi[k] = s->root_bounds[3 + k]; }
+        v.n_branches = lay.n_branches; v.n_tris = s->n_tris; v.n_mats = s->n_mats;
+        v.root_is_leaf = (s->nodes[0].b & SQT_NODE_LEAF) ? 1u : 0u;
+        v.planes_finite = (uint32_t)lay.planes_finite;
+        c->sc = v; c->has_scene = true; c->terminate_on_black_ok = lay.terminate_on_black_ok; c->tree_height = lay.height;
+        c->upload_bytes = (uint64_t)s->n_tris * 48 + lay.nodes.size() * 16 + lay.boxes.size() * 16 + lay.mats.size() * 16 + ranges.size() * 8 + 8;
+        c->upload_layout_ms = t1 - t0;
+        c->upload_ms = now_ms() - t0;
+    }
+    return SQT_OK;
+}
 
-    free_scene(ctx);
-    CU(cudaMalloc(&ctx->d_nodes, dn.size() * sizeof(float4)));
-    CU(cudaMalloc(&ctx->d_tris, (size_t)(s->n_tris ? s->n_tris : 1) * 48));
-    CU(cudaMalloc(&ctx->d_mats, dm.size() * sizeof(float4)));
-    CU(cudaMalloc(&ctx->d_leaves, lay.leaves.size() * sizeof(float4)));
-    CU(cudaMemcpyAsync(ctx->d_leaves, lay.leaves.data(), lay.leaves.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_nodes, dn.data(), dn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    if (s->n_tris) CU(cudaMemcpyAsync(ctx->d_tris, s->tris, (size_t)s->n_tris * 48, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_mats, dm.data(), dm.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    SceneView v = {};
-    v.nodes = ctx->d_nodes; v.tris = ctx->d_tris; v.mats = ctx->d_mats; v.leaves = ctx->d_leaves;
-    v.leaf_cull = (uint32_t)ctx->leaf_cull;
-    for (int k = 0; k < 3; ++k) { v.root_lo[k] = s->root_bounds[k]; v.root_hi[k] = s->root_bounds[3 + k]; }
-    v.n_branches = n_br; v.n_tris = s->n_tris; v.n_mats = s->n_mats;
-    v.root_is_leaf = (s->nodes[0].b & SQT_NODE_LEAF) ? 1u : 0u;
-    ctx->sc = v; ctx->has_scene = true; ctx->terminate_on_black_ok = tob; ctx->tree_height = height;
+extern "C" int sqt_upload_scene(sqt_ctx *ctx, const sqt_scene_desc *s) {
+    if (!ctx || !s) return SQT_E_INVALID;
+    return upload_scene_to(&ctx, 1, s);
+}
+
+// the same scene onto every context of a single-process group: the tree is walked once, every staged chunk of
+// triangles goes to all devices
+extern "C" int sqt_upload_scene_group(sqt_ctx **ctxs, int n, const sqt_scene_desc *s) {
+    if (!ctxs || n < 1 || !s) return SQT_E_INVALID;
+    for (int i = 0; i < n; ++i) if (!ctxs[i]) return SQT_E_INVALID;
+    return upload_scene_to(ctxs, n, s);
+}
+
+extern "C" int sqt_last_upload(const sqt_ctx *ctx, uint64_t *h2d_bytes, double *wall_ms, double *host_layout_ms) {
+    if (!ctx) return SQT_E_INVALID;
+    if (h2d_bytes) *h2d_bytes = ctx->upload_bytes;
+    if (wall_ms) *wall_ms = ctx->upload_ms;
+    if (host_layout_ms) *host_layout_ms = ctx->upload_layout_ms;
     return SQT_OK;
 }
 
@@ -768,9 +400,12 @@ static int persistent_grid(sqt_ctx *ctx, K kernel, long long nwork) {
     if (want < grid) grid = want ? want : 1;
     return (int)grid;
 }
+// k_paths_pool launch shape + the per-slot global state it needs.  `launch` false: only size the grid and make sure the
+// allocations exist (the pre-pass of a render, so that nothing can fail between the ranks' agreement and the collective).
+struct PoolPlan { int grid = 0; size_t smem = 0; int depth = 1, pm_stride = 8; };
 template <bool COUNT, int K>
-static int launch_pool(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems) {
-    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 32) * sizeof(uint32_t);
+static int pool_step(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems, bool launch) {
+    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 3 * (32 * K / 4)) * sizeof(uint32_t);
     auto kern = k_paths_pool<COUNT, K>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -785,34 +420,35 @@ static int launch_pool(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd,
     long long grid = (long long)ctx->sm_count * per_sm, want = (nitems + 128 * K - 1) / (128 * K);
     if (want < grid) grid = want ? want : 1;
     const long long slots = grid * 4 * 32 * K;
-    if (slots > ctx->cap_pool_slots) {
-        cudaFree(ctx->d_gstack); cudaFree(ctx->d_gpm); cudaFree(ctx->d_gpath);
-        ctx->d_gstack = nullptr; ctx->d_gpm = nullptr; ctx->d_gpath = nullptr; ctx->cap_pool_slots = 0;
-        const long long cap = (long long)ctx->sm_count * 16 * 4 * 32 * K > slots ? (long long)ctx->sm_count * 16 * 4 * 32 * K : slots;
-        CU(cudaMalloc(&ctx->d_gstack, (size_t)cap * kStackWords * sizeof(uint32_t)));
-        CU(cudaMalloc(&ctx->d_gpm, (size_t)cap * SQT_MAX_DEPTH * sizeof(uint16_t)));
-        CU(cudaMalloc(&ctx->d_gpath, (size_t)cap * 2 * sizeof(uint4)));
-        ctx->cap_pool_slots = cap;
-    }
-    // a ray's stack holds at most one 3-word entry per branch on a root-to-leaf path: pack the slots' stacks that tightly
-    // (32-byte granules) so that the stacks of all resident slots stay in L2
-    int stride = (int)((3u * ctx->tree_height + 7u) & ~7u);
-    if (stride > kStackWords) stride = kStackWords;
-    if (stride < 8) stride = 8;
+    // a ray's stack holds at most one 16-byte entry per branch on a root-to-leaf path; the stacks of a warp's slots are
+    // interleaved entry by entry, so the few entries in use of all resident slots share cache lines and stay in L2
+    int depth = (int)ctx->tree_height;
+    if (depth > kStackEntries) depth = kStackEntries;
+    if (depth < 1) depth = 1;
     // the per-path material list of a slot: max_depth entries, packed (16-byte granules) for the same reason
     int pm_stride = (d.max_depth + 7) & ~7;
     if (pm_stride > SQT_MAX_DEPTH) pm_stride = SQT_MAX_DEPTH;
-    kern<<<(int)grid, 128, smem, ctx->stream>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->pool_tune, ctx->d_gstack, ctx->d_gpm, ctx->d_gpath, stride, pm_stride);
+    if (slots > ctx->cap_pool_slots || slots * depth > ctx->cap_stack_entries) {
+        cudaFree(ctx->d_gstack); cudaFree(ctx->d_gpm); cudaFree(ctx->d_gpath);
+        ctx->d_gstack = nullptr; ctx->d_gpm = nullptr; ctx->d_gpath = nullptr; ctx->cap_pool_slots = 0; ctx->cap_stack_entries = 0;
+        const long long cap = (long long)ctx->sm_count * 16 * 4 * 32 * K > slots ? (long long)ctx->sm_count * 16 * 4 * 32 * K : slots;
+        CU(cudaMalloc(&ctx->d_gstack, (size_t)cap * depth * sizeof(float4)));
+        CU(cudaMalloc(&ctx->d_gpm, (size_t)cap * SQT_MAX_DEPTH * sizeof(uint16_t)));
+        CU(cudaMalloc(&ctx->d_gpath, (size_t)cap * 2 * sizeof(uint4)));
+        ctx->cap_pool_slots = cap; ctx->cap_stack_entries = cap * depth;
+    }
+    if (!launch) return SQT_OK;
+    kern<<<(int)grid, 128, smem, ctx->stream>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->pool_tune, ctx->d_gstack, ctx->d_gpm, ctx->d_gpath, depth, pm_stride);
     CU(cudaGetLastError());
     return SQT_OK;
 }
 template <bool COUNT>
-static int launch_pool_k(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems) {
+static int pool_step_k(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems, bool launch) {
     switch (ctx->pool_k) {
-    case 1: return launch_pool<COUNT, 1>(ctx, d, rd, round, nitems);
-    case 2: return launch_pool<COUNT, 2>(ctx, d, rd, round, nitems);
-    case 3: return launch_pool<COUNT, 3>(ctx, d, rd, round, nitems);
-    default: return launch_pool<COUNT, 4>(ctx, d, rd, round, nitems);
+    case 1: return pool_step<COUNT, 1>(ctx, d, rd, round, nitems, launch);
+    case 2: return pool_step<COUNT, 2>(ctx, d, rd, round, nitems, launch);
+    case 3: return pool_step<COUNT, 3>(ctx, d, rd, round, nitems, launch);
+    default: return pool_step<COUNT, 4>(ctx, d, rd, round, nitems, launch);
     }
 }
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
@@ -887,16 +523,69 @@ static RenderParams to_device_params(const sqt_ctx *ctx, const sqt_camera *cam, 
     return d;
 }
 
-// Enqueue all kernels of one render on ctx->stream (no host sync).  Events: 0 start, 1 after primary,
-// 2 after paths, 3 after reduce, 4 after tonemap.
-static int enqueue_render(sqt_ctx *ctx, const RenderParams &d, bool count, uint32_t *launches) {
+// Everything of a render that can fail for lack of memory or because of its arguments, done BEFORE any kernel or
+// collective is enqueued: image buffers, the sample buffer of a round, the pool slots' global state.
+struct RenderPlan { long long nwork = 0; int k0 = 0, k1 = 0, log2_s = 0; long long sbytes = 0; };
+static int prepare_render(sqt_ctx *ctx, const RenderParams &d, bool count, bool host_image, RenderPlan &pl) {
     const long long npix = (long long)d.rows * d.cols;
     int rc = ensure_image(ctx, npix); if (rc) return rc;
+    if (host_image) { rc = ensure_host_image(ctx, npix); if (rc) return rc; }
+    pl.nwork = work_items(d);
+    if (d.mode == 1) return SQT_OK;
+    sample_range(d, pl.k0, pl.k1);
+    pl.log2_s = round_log2_s(pl.nwork, pl.k1 - pl.k0 > 0 ? pl.k1 - pl.k0 : 1, ctx->sbuf_budget);
+    const int S = 1 << pl.log2_s;
+    if ((pl.k1 - pl.k0 + S - 1) / S > 256) return fail(ctx, SQT_E_UNSUPPORTED, "more than 256 sample rounds (raise SQT_SBUF_MB)");
+    pl.sbytes = pl.nwork * (long long)S * 12ll;
+    rc = ensure_sbuf(ctx, pl.sbytes > 0 ? pl.sbytes : 12); if (rc) return rc;
+    if (ctx->pool_k > 0) {
+        RoundInfo none = {};
+        rc = count ? pool_step_k<true>(ctx, d, none, 0, pl.nwork << pl.log2_s, false) : pool_step_k<false>(ctx, d, none, 0, pl.nwork << pl.log2_s, false);
+        if (rc) return rc;
+    }
+    return SQT_OK;
+}
+
+// Multi-rank contexts: all ranks learn whether every rank got through check_params + prepare_render, with a one-word
+// ncclAllReduce(max) -- a collective every rank reaches whatever happened to it locally.  Only if all agree is the
+// frame (and its ncclReduce) enqueued; otherwise every rank returns an error and nobody waits in a collective.
+static int group_agree(sqt_ctx *ctx, int rc_local) {
+    if (ctx->world <= 1 || !ctx->comm) return rc_local;
+    if (ctx->comm_broken) return fail(ctx, SQT_E_NCCL, "the communicator of this group was aborted after an earlier failure");
+    NcclApi *na = nccl_api();
+    const std::string local_err = ctx->err;
+    cudaSetDevice(ctx->device);
+    uint32_t *flag = ctx->d_flag + 1;
+    const uint32_t v = rc_local ? 1u : 0u;
+    uint32_t out = 1u;
+    cudaError_t e = cudaMemcpyAsync(flag, &v, 4, cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t r = e == cudaSuccess ? na->AllReduce(flag, flag, 1, kNcclInt32, kNcclMax, ctx->comm, ctx->stream) : 1;
+    if (r == 0) e = cudaMemcpyAsync(&out, flag, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (r == 0 && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (r != 0 || e != cudaSuccess) {
+        na->CommAbort(ctx->comm); ctx->comm_broken = true;
+        return fail(ctx, SQT_E_NCCL, "group agreement failed (%s); communicator aborted", r ? na->GetErrorString(r) : cudaGetErrorString(e));
+    }
+    if (rc_local) { ctx->err = local_err; return rc_local; }
+    if (out) return fail(ctx, SQT_E_NCCL, "another rank of the group could not start this render; nothing was enqueued");
+    return SQT_OK;
+}
+// a failure after the agreement (a launch error) would leave the other ranks waiting in ncclReduce: abort the communicator
+static int group_abort(sqt_ctx *ctx, int rc) {
+    if (rc && ctx->world > 1 && ctx->comm && !ctx->comm_broken) { nccl_api()->CommAbort(ctx->comm); ctx->comm_broken = true; }
+    return rc;
+}
+
+// Enqueue all kernels of one render on ctx->stream (no host sync, no allocation).  Events: 0 start, 1 after primary,
+// 2 after paths, 3 after reduce, 4 after tonemap.
+static int enqueue_render(sqt_ctx *ctx, const RenderParams &d, bool count, const RenderPlan &pl, uint32_t *launches) {
+    const long long npix = (long long)d.rows * d.cols;
+    int rc = SQT_OK;
     cudaStream_t st = ctx->stream;
     CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), st));
     CU(cudaMemsetAsync(ctx->d_accum, 0, (size_t)npix * 3 * sizeof(float), st));
     CU(cudaEventRecord(ctx->ev[0], st));
-    const long long nwork = work_items(d);
+    const long long nwork = pl.nwork;
     uint32_t nl = 0;
     if (d.mode == 1) {
         CU(cudaEventRecord(ctx->ev[1], st));
@@ -911,17 +600,13 @@ static int enqueue_render(sqt_ctx *ctx, const RenderParams &d, bool count, uint3
         }
         CU(cudaEventRecord(ctx->ev[1], st));
         // rounds of S samples per pixel: trace (persistent lanes, one counter per round), then add in sample order
-        int k0, k1;
-        sample_range(d, k0, k1);
+        const int k0 = pl.k0, k1 = pl.k1;
         RoundInfo rd = {};
         rd.pixel_list = d.primary_reuse ? ctx->d_pixel_list : nullptr;
         rd.prim = d.primary_reuse ? ctx->d_prim : nullptr;
         rd.n_slots = nwork; rd.slot_stride = nwork;
-        rd.log2_s = round_log2_s(nwork, k1 - k0 > 0 ? k1 - k0 : 1, ctx->sbuf_budget);
+        rd.log2_s = pl.log2_s;
         const int S = 1 << rd.log2_s;
-        if ((k1 - k0 + S - 1) / S > 256) return fail(ctx, SQT_E_UNSUPPORTED, "more than 256 sample rounds (raise SQT_SBUF_MB)");
-        const long long sbytes = nwork * (long long)S * 12ll;
-        rc = ensure_sbuf(ctx, sbytes); if (rc) return rc;
         rd.sbuf = ctx->d_sbuf;
         const int agrid = (int)((nwork + 255) / 256 < (long long)ctx->sm_count * 8 ? (nwork + 255) / 256 : (long long)ctx->sm_count * 8);
         int round = 0;
@@ -929,7 +614,7 @@ static int enqueue_render(sqt_ctx *ctx, const RenderParams &d, bool count, uint3
             rd.k0 = kb; rd.k1 = kb + S < k1 ? kb + S : k1;
             CU(cudaMemsetAsync(ctx->d_sbuf, 0, (size_t)(nwork * (long long)(rd.k1 - rd.k0) * 12ll), st));
             if (ctx->pool_k > 0) {
-                rc = count ? launch_pool_k<true>(ctx, d, rd, round, nwork << rd.log2_s) : launch_pool_k<false>(ctx, d, rd, round, nwork << rd.log2_s);
+                rc = count ? pool_step_k<true>(ctx, d, rd, round, nwork << rd.log2_s, true) : pool_step_k<false>(ctx, d, rd, round, nwork << rd.log2_s, true);
                 if (rc) return rc;
             } else if (count) k_paths<true><<<persistent_grid(ctx, k_paths<true>, nwork << rd.log2_s), 128, 0, st>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->tune);
             else k_paths<false><<<persistent_grid(ctx, k_paths<false>, nwork << rd.log2_s), 128, 0, st>>>(ctx->sc, d, rd, round, ctx->d_stats, ctx->tune);
@@ -974,12 +659,15 @@ static void fill_stats(sqt_ctx *ctx, sqt_stats *s, uint32_t launches) {
 
 extern "C" int sqt_render_resident(sqt_ctx *ctx, const sqt_camera *cam, const sqt_render_params *p, sqt_stats *stats) {
     if (!ctx) return SQT_E_INVALID;
-    int rc = check_params(ctx, cam, p); if (rc) return rc;
     if (stats) memset(stats, 0, sizeof *stats);
-    CU(cudaSetDevice(ctx->device));
-    const RenderParams d = to_device_params(ctx, cam, p);
+    cudaSetDevice(ctx->device);
+    RenderParams d = {};
+    RenderPlan pl;
+    int rc = check_params(ctx, cam, p);
+    if (!rc) { d = to_device_params(ctx, cam, p); rc = prepare_render(ctx, d, (p->flags & SQT_F_COUNT_WORK) != 0, false, pl); }
+    rc = group_agree(ctx, rc); if (rc) return rc;
     uint32_t nl = 0;
-    rc = enqueue_render(ctx, d, (p->flags & SQT_F_COUNT_WORK) != 0, &nl); if (rc) return rc;
+    rc = enqueue_render(ctx, d, (p->flags & SQT_F_COUNT_WORK) != 0, pl, &nl); if (rc) return group_abort(ctx, rc);
     CU(cudaStreamSynchronize(ctx->stream));
     fill_stats(ctx, stats, nl);
     return SQT_OK;
@@ -1002,14 +690,16 @@ extern "C" int sqt_download_image(sqt_ctx *ctx, uint8_t *rgb8_out, float *accum_
 extern "C" int sqt_render(sqt_ctx *ctx, const sqt_camera *cam, const sqt_render_params *p, uint8_t *rgb8_out,
                           float *accum_out, sqt_stats *stats) {
     if (!ctx) return SQT_E_INVALID;
-    int rc = check_params(ctx, cam, p); if (rc) return rc;
     if (stats) memset(stats, 0, sizeof *stats);
-    CU(cudaSetDevice(ctx->device));
-    const RenderParams d = to_device_params(ctx, cam, p);
+    cudaSetDevice(ctx->device);
+    RenderParams d = {};
+    RenderPlan pl;
+    int rc = check_params(ctx, cam, p);
+    if (!rc) { d = to_device_params(ctx, cam, p); rc = prepare_render(ctx, d, (p->flags & SQT_F_COUNT_WORK) != 0, true, pl); }
+    rc = group_agree(ctx, rc); if (rc) return rc;
     const long long npix = (long long)d.rows * d.cols;
-    rc = ensure_host_image(ctx, npix); if (rc) return rc;
     uint32_t nl = 0;
-    rc = enqueue_render(ctx, d, (p->flags & SQT_F_COUNT_WORK) != 0, &nl); if (rc) return rc;
+    rc = enqueue_render(ctx, d, (p->flags & SQT_F_COUNT_WORK) != 0, pl, &nl); if (rc) return group_abort(ctx, rc);
     cudaStream_t st = ctx->stream;
     const bool root = ctx->rank == 0;
     CU(cudaEventRecord(ctx->ev[5], st));

@@ -50,37 +50,43 @@ struct alignas(8) int2 { int x, y; };
 namespace sqt {
 
 // ---------------------------------------------------------------------------- device records
-// Branch node, 64 B = 4 x 128-bit loads.  `lo`/`hi` are the node's own clipped box, i.e. the `bbox`
-// argument intersectBIH' receives for this node (BIH.hs:111,130-141); Lhi = hi with hi[axis] := lmax is
-// the upper corner of the left child's box, Rlo = lo with lo[axis] := rmin the lower corner of the right
-// child's box.  All are static properties of the tree, derived at upload time by copying planes (no
-// arithmetic).  Storing both corners makes the two child slab tests axis-free (no per-lane selects).
-//   q0 = (lo.x, lo.y, lo.z, hi.x)   q1 = (hi.y, hi.z, Lhi.x, Lhi.y)   q2 = (Lhi.z, Rlo.x, Rlo.y, Rlo.z)
-//   q3 = (left, right, lmeta, rmeta) as u32 bits:
-//        child is Branch: ref = index into the branch array, meta = 0
-//        child is Leaf  : ref = index into the leaf array,   meta = kLeaf | count
-// Leaf record, 32 B = 2 x 128-bit loads: the TIGHT bounding box of the leaf's triangles and their longest
-// edge, used only by the conservative leaf culling below (never by the reference algorithm):
-//   b0 = (lo.x, lo.y, lo.z, hi.x)   b1 = (hi.y, hi.z, longest edge E, first triangle as u32 bits)
-//        lmeta additionally carries the split axis in bits 27..28
-// Traversal stack entries (the top word tells them apart):
-//   phase A (near subtree in flight), 1 word : index of the branch (< 2^30, so kPhaseB is clear); plane, far child and
-//                                              its meta are re-read from the node when the near subtree returns
-//   phase B (near hit parked, far subtree in flight), 3 words : { t bits, dist bits, tri | kPhaseB }
+// Branch node, 16 B = ONE 128-bit load: exactly the reference's BIHN (BIH.hs:37) plus the two child references:
+//   (lmax, rmin, L, R)      L = kLeaf? | kSlow? | axis << 28 | index      R = kLeaf? | index
+// index = position in the branch array (child is a Branch) or in the leaf array (child is a Leaf), < 2^28.
+// The traversal carries the ray's parametric interval (tmin, tmax) through the box of the subtree it is about to
+// enter -- the two numbers intersectsBB (Geometry.hs:166-177) computes for that box -- and updates it per visit from
+// the ONE plane in which a child box differs from its parent (BIH.hs:130-141): the classic BIH step.  That is exact
+// (same compare results as recomputing all six slabs, see desc_step) whenever the child box is nested in the parent's
+// on the split axis, lo[ax] <= lmax <= hi[ax] and lo[ax] <= rmin <= hi[ax]; lmax/rmin carry +-0.001 (BIH.hs:93-95), so
+// a plane can stick out of the clipped box -- such nodes are flagged kSlow at upload and, like rays with a
+// zero/denormal/non-finite component, take the literal six-slab path from the node's box in the side array `boxes`.
+// Box of a branch (side array, slow path only), 32 B: c0 = (lo.x, lo.y, lo.z, hi.x)  c1 = (hi.y, hi.z, -, -): the
+// `bbox` argument intersectBIH' receives for this node, derived at upload by copying planes (no arithmetic).
+// Leaf record, 32 B = 2 x 128-bit loads: the TIGHT bounding box of the leaf's triangles and their longest edge
+// (used only by the conservative leaf culling, never by the reference algorithm) and the triangle range:
+//   b0 = (lo.x, lo.y, lo.z, hi.x)   b1 = (hi.y, hi.z, longest edge E, first | min(count, 31) << 27 as u32 bits)
+//        a leaf of 31 or more triangles keeps its count in the spare word of its first triangle record
+// Traversal stack entries, 16 B each (one 128-bit load/store), at most one per tree level:
+//   phase A (near subtree in flight) : (far child ref | axis << 28, far tmin, far tmax, plane isClose compares with)
+//   phase B (near hit parked, far subtree in flight) : (tri | kPhaseB, t, dist, -)
 constexpr uint32_t kLeaf = 0x80000000u;
 constexpr uint32_t kPhaseB = 0x40000000u;
-constexpr uint32_t kAxisShift = 27;
-constexpr uint32_t kCountMask = 0x07ffffffu;
-constexpr int kNodeQuads = 4;
-constexpr int kStackWords = 3 * 48;            // at most one entry (1 or 3 words) per tree level
+constexpr uint32_t kSlow = 0x40000000u;
+constexpr uint32_t kAxisShift = 28;
+constexpr uint32_t kIdxMask = 0x0fffffffu;
+constexpr uint32_t kLeafFirstMask = 0x07ffffffu;
+constexpr uint32_t kLeafCountShift = 27;
+constexpr uint32_t kLeafLong = 31u;
+constexpr int kStackEntries = 48;              // at most one entry per tree level (SQT_MAX_HEIGHT)
 #ifndef SQT_MAX_DEPTH
 #define SQT_MAX_DEPTH 64
 #endif
 
 struct SceneView {
-    const float4 *nodes;     // kNodeQuads float4 per branch
+    const float4 *nodes;     // 1 float4 per branch
+    const float4 *boxes;     // 2 float4 per branch (slow path only)
     const float4 *leaves;    // 2 float4 per leaf
-    const float4 *tris;      // 3 float4 per triangle: (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z, mat, orig, pad)
+    const float4 *tris;      // 3 float4 per triangle: (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z, mat, orig, leaf count if >= 31)
     const float4 *mats;      // 3 float4 per material: (refl, surf.rgb) (emissive, emit.rgb) (ec.rgb, flags)
     const float4 *spheres;   // extension: 2 float4 per sphere: (center.xyz, radius) (material bits, -, -, -)
     uint32_t n_spheres;
@@ -88,6 +94,7 @@ struct SceneView {
     uint32_t n_branches, n_tris, n_mats;
     uint32_t root_is_leaf;   // tree = Leaf: no box test at all (BIH.hs:105)
     uint32_t leaf_cull;      // 1 = skip leaves whose enlarged tight box the ray provably misses (exact, see enter_leaf)
+    uint32_t planes_finite;  // every plane and box coordinate of the tree is finite (else every ray takes the literal path)
 };
 
 struct Ray { float ox, oy, oz, dx, dy, dz; };
@@ -125,15 +132,28 @@ SQT_HD float dot3(float a, float b, float c, float d, float e, float f) {
 }
 
 // ------------------------------------------------------------------------------- slab tests
-// Geometry.hs:166-177, literal (used for the root box and for rays where a NaN can appear)
+// Geometry.hs:166-177, literal: also returns the two numbers the test compares.  `fast` (the ray cannot produce a NaN
+// slab value: all of origin, direction and 1/direction finite, all planes finite) uses the hardware FMNMX -- without
+// NaNs min/max are exact, order-free selections whose zero sign never reaches the two comparisons; otherwise the
+// Haskell class defaults decide (operand order matters with NaN).
+SQT_HD bool slab_iv(float lx, float ly, float lz, float hx, float hy, float hz, const Ray &r, float dfx, float dfy, float dfz,
+                    bool fast, float &tmin, float &tmax) {
+    const float t1 = XMUL(XSUB(lx, r.ox), dfx), t2 = XMUL(XSUB(hx, r.ox), dfx);
+    const float t3 = XMUL(XSUB(ly, r.oy), dfy), t4 = XMUL(XSUB(hy, r.oy), dfy);
+    const float t5 = XMUL(XSUB(lz, r.oz), dfz), t6 = XMUL(XSUB(hz, r.oz), dfz);
+    if (fast) {
+        tmin = SQT_FMAX(SQT_FMAX(SQT_FMIN(t1, t2), SQT_FMIN(t3, t4)), SQT_FMIN(t5, t6));
+        tmax = SQT_FMIN(SQT_FMIN(SQT_FMAX(t1, t2), SQT_FMAX(t3, t4)), SQT_FMAX(t5, t6));
+    } else {
+        tmin = hs_max(hs_max(hs_min(t1, t2), hs_min(t3, t4)), hs_min(t5, t6));
+        tmax = hs_min(hs_min(hs_max(t1, t2), hs_max(t3, t4)), hs_max(t5, t6));
+    }
+    return tmax > 0.0f && tmin < tmax;
+}
 SQT_HD bool slab_exact(float lx, float ly, float lz, float hx, float hy, float hz, const Ray &r,
                        float dfx, float dfy, float dfz) {
-    float t1 = XMUL(XSUB(lx, r.ox), dfx), t2 = XMUL(XSUB(hx, r.ox), dfx);
-    float t3 = XMUL(XSUB(ly, r.oy), dfy), t4 = XMUL(XSUB(hy, r.oy), dfy);
-    float t5 = XMUL(XSUB(lz, r.oz), dfz), t6 = XMUL(XSUB(hz, r.oz), dfz);
-    float tmin = hs_max(hs_max(hs_min(t1, t2), hs_min(t3, t4)), hs_min(t5, t6));
-    float tmax = hs_min(hs_min(hs_max(t1, t2), hs_max(t3, t4)), hs_max(t5, t6));
-    return tmax > 0.0f && tmin < tmax;
+    float tmin, tmax;
+    return slab_iv(lx, ly, lz, hx, hy, hz, r, dfx, dfy, dfz, false, tmin, tmax);
 }
 
 // branch-free 3-way select (the compiler turns the ?: chain into divergent branches otherwise)
@@ -147,29 +167,6 @@ SQT_HD float sel3(int ax, float x, float y, float z) {
 #else
     return ax == 0 ? x : (ax == 1 ? y : z);
 #endif
-}
-
-// Both child boxes of a branch (BIH.hs:128-141): left = (lo, Lhi), right = (Rlo, hi).  `safe` rays (all
-// 1/dir finite, origin finite) cannot produce a NaN slab value, and without NaNs min/max are exact,
-// order-free operations whose zero sign never reaches the two comparisons -- so the hardware FMNMX path is
-// used.  Unsafe rays take the literal Geometry.hs:166-177 path.
-SQT_HD void slab_children(const float4 &q0, const float4 &q1, const float4 &q2, const Ray &r, float dfx, float dfy,
-                          float dfz, bool safe, bool &hit_l, bool &hit_r) {
-    if (safe) {
-        const float lx = XMUL(XSUB(q0.x, r.ox), dfx), ly = XMUL(XSUB(q0.y, r.oy), dfy), lz = XMUL(XSUB(q0.z, r.oz), dfz);
-        const float hx = XMUL(XSUB(q0.w, r.ox), dfx), hy = XMUL(XSUB(q1.x, r.oy), dfy), hz = XMUL(XSUB(q1.y, r.oz), dfz);
-        const float ax_ = XMUL(XSUB(q1.z, r.ox), dfx), ay = XMUL(XSUB(q1.w, r.oy), dfy), az = XMUL(XSUB(q2.x, r.oz), dfz);
-        const float bx = XMUL(XSUB(q2.y, r.ox), dfx), by = XMUL(XSUB(q2.z, r.oy), dfy), bz = XMUL(XSUB(q2.w, r.oz), dfz);
-        const float tmin_l = SQT_FMAX(SQT_FMAX(SQT_FMIN(lx, ax_), SQT_FMIN(ly, ay)), SQT_FMIN(lz, az));
-        const float tmax_l = SQT_FMIN(SQT_FMIN(SQT_FMAX(lx, ax_), SQT_FMAX(ly, ay)), SQT_FMAX(lz, az));
-        const float tmin_r = SQT_FMAX(SQT_FMAX(SQT_FMIN(bx, hx), SQT_FMIN(by, hy)), SQT_FMIN(bz, hz));
-        const float tmax_r = SQT_FMIN(SQT_FMIN(SQT_FMAX(bx, hx), SQT_FMAX(by, hy)), SQT_FMAX(bz, hz));
-        hit_l = tmax_l > 0.0f && tmin_l < tmax_l;
-        hit_r = tmax_r > 0.0f && tmin_r < tmax_r;
-    } else {
-        hit_l = slab_exact(q0.x, q0.y, q0.z, q1.z, q1.w, q2.x, r, dfx, dfy, dfz);
-        hit_r = slab_exact(q2.y, q2.z, q2.w, q0.w, q1.x, q1.y, r, dfx, dfy, dfz);
-    }
 }
 
 // ------------------------------------------------------------------------- Moller-Trumbore
@@ -211,37 +208,86 @@ SQT_HD bool moller_trumbore(const float4 &a0, const float4 &a1, const float4 &a2
     return true;
 }
 
+// ------------------------------------------------------------------------------ leaf records
+// Leaf record (see "device records") of the leaf tris[first .. first + cnt): the tight box of the triangles as
+// Moller-Trumbore sees them (v0, v0 + e1, v0 + e2), rounded outwards, and their longest edge, rounded up.  Used only by
+// the conservative leaf culling.  Runs on the device at upload (k_leaf_records) and on the host in tests/emu.
+SQT_HD_NOINLINE inline void make_leaf_record(const float4 *tris, uint32_t first, uint32_t cnt, float4 &b0, float4 &b1) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, e2max = 0;
+    for (uint32_t t = 0; t < cnt; ++t) {
+        const float4 a0 = tris[3 * (size_t)(first + t)], a1 = tris[3 * (size_t)(first + t) + 1], a2 = tris[3 * (size_t)(first + t) + 2];
+        const float v0[3] = {a0.x, a0.y, a0.z}, e1[3] = {a0.w, a1.x, a1.y}, e2[3] = {a1.z, a1.w, a2.x};
+        double l1 = 0, l2 = 0, l3 = 0;
+        for (int k = 0; k < 3; ++k) {
+            const double v[3] = {(double)v0[k], (double)v0[k] + e1[k], (double)v0[k] + e2[k]};
+            for (int q = 0; q < 3; ++q) { if (v[q] < lo[k]) lo[k] = v[q]; if (v[q] > hi[k]) hi[k] = v[q]; }
+            l1 += (double)e1[k] * e1[k]; l2 += (double)e2[k] * e2[k];
+            l3 += ((double)e2[k] - e1[k]) * ((double)e2[k] - e1[k]);
+        }
+        e2max = fmax(e2max, fmax(l1, fmax(l2, l3)));
+    }
+    if (cnt == 0) { for (int k = 0; k < 3; ++k) lo[k] = hi[k] = 0; }
+    const uint32_t c5 = cnt < kLeafLong ? cnt : kLeafLong;
+    b0.x = nextafterf((float)lo[0], -INFINITY); b0.y = nextafterf((float)lo[1], -INFINITY); b0.z = nextafterf((float)lo[2], -INFINITY);
+    b0.w = nextafterf((float)hi[0], INFINITY);
+    b1.x = nextafterf((float)hi[1], INFINITY); b1.y = nextafterf((float)hi[2], INFINITY);
+    b1.z = nextafterf((float)sqrt(e2max), INFINITY);
+    b1.w = u2f((cnt ? first : 0u) | (c5 << kLeafCountShift));
+}
+
 // ------------------------------------------------------------------------------ traversal
 // intersectBIH (BIH.hs:101-141) as an explicit-stack state machine that visits exactly the
 // subtrees the recursion visits, in the same order, and combines results with the same rules:
 //   * the own-box test of BIH.hs:112 is evaluated for the root only -- for every other branch it
 //     repeats, with identical operands, the test its parent just passed at BIH.hs:128-129;
-//   * a branch whose two children are both hit pushes one word (its index, "phase A") and enters
-//     the near child; when that subtree returns, isClose (BIH.hs:121-123) is evaluated on the near
-//     subtree's OWN result; if the far child must still be visited and near had a hit, that hit is
-//     parked on the stack ("phase B", 3 words) and merged with min' when the far subtree returns.
+//   * a branch whose two children are both hit pushes a "phase A" entry (far child, its interval, the plane
+//     isClose looks at) and enters the near child; when that subtree returns, isClose (BIH.hs:121-123) is evaluated
+//     on the near subtree's OWN result; if the far child must still be visited and near had a hit, that hit is
+//     parked in the same stack slot ("phase B") and merged with min' when the far subtree returns.
 //
-// The machine is cut into three kinds of unit step so that a warp can run them in lock step
-// (sqt_backend.cu: all lanes do traversal steps together, then all lanes do triangle steps together):
-//   ST_DESC  enter subtree (child, meta), a Branch: test both child boxes, pick the next subtree
-//   ST_ENTER enter subtree (child, meta), a Leaf: fetch its record, (conservatively) cull it or become ST_LEAF
+// The machine is cut into unit steps so that a warp can run them in lock step (sqt_kernels.cuh):
+//   ST_DESC  enter Branch `child` with the ray's interval (tmin, tmax) through its box: derive both child intervals
+//   ST_ENTER enter Leaf `child`: fetch its record, (conservatively) cull it or become ST_LEAF
 //   ST_LEAF  test ONE triangle of the current leaf, walking from the last to the first
-//   ST_RET   a subtree returned `cur`: pop ONE stack entry and act on it
+//   ST_RET   a subtree returned `cur`: pop stack entries until one sends the ray into a far subtree
 //   ST_DONE  the ray is finished, result in `cur`
 enum : int { ST_DONE = 0, ST_DESC = 1, ST_LEAF = 2, ST_RET = 3, ST_EXIT = 4, ST_ENTER = 5 };
 
 struct TravLane {
     Ray r;
     float dfx, dfy, dfz;        // 1/dir (Geometry.hs:168), IEEE
-    uint32_t child, meta;       // ST_DESC: subtree to enter ; ST_LEAF: child = first triangle of the leaf
+    uint32_t child;             // ST_DESC: branch to visit ; ST_ENTER: leaf to enter ; ST_LEAF: first triangle of the leaf
+    float tmin, tmax;           // ST_DESC: intersectsBB's two numbers for the box of `child` (fast rays only)
     int i;                      // ST_LEAF: offset of the next triangle to test (counts down to 0)
     Hit cur;                    // result of the subtree that just returned / running best of the current leaf
-    int sp;
+    int sp;                     // stack entries in use
     int state;
     uint32_t sgn;               // bit k set iff dir[k] > 0 (leftToRight on axis k, BIH.hs:127)
-    float dfac;                 // |d|_1 * (1 + |d|_1), factor of the leaf-culling error bound
-    bool safe;
-    uint32_t *stack;            // kStackWords words of lane-private (local) memory, owned by the caller
+    bool safe;                  // no slab value of this ray can be NaN -> interval stepping + FMNMX
+    float4 *stack;              // entry e lives at stack[e * STRIDE] (STRIDE template parameter of the steps)
+};
+
+// How a step reads the ray: from the lane's registers (one ray per lane) ...
+struct LaneRay {
+    const TravLane &L;
+    SQT_HD explicit LaneRay(const TravLane &l) : L(l) {}
+    SQT_HD float o(int ax) const { return sel3(ax, L.r.ox, L.r.oy, L.r.oz); }
+    SQT_HD float d(int ax) const { return sel3(ax, L.r.dx, L.r.dy, L.r.dz); }
+    SQT_HD float df(int ax) const { return sel3(ax, L.dfx, L.dfy, L.dfz); }
+    SQT_HD Ray ray() const { return L.r; }
+    SQT_HD void dfv(float &x, float &y, float &z) const { x = L.dfx; y = L.dfy; z = L.dfz; }
+};
+// ... or from a structure-of-arrays pool (k_paths_pool: word f of slot s at base[f * stride + s]; fields ox oy oz dx dy
+// dz dfx dfy dfz are the first nine): the split axis indexes the array, no selects, no ray registers held over a burst
+struct PoolRay {
+    const uint32_t *base; int stride;
+    SQT_HD PoolRay(const uint32_t *b, int st) : base(b), stride(st) {}
+    SQT_HD float f(int k) const { return u2f(base[k * stride]); }
+    SQT_HD float o(int ax) const { return f(ax); }
+    SQT_HD float d(int ax) const { return f(3 + ax); }
+    SQT_HD float df(int ax) const { return f(6 + ax); }
+    SQT_HD Ray ray() const { Ray r; r.ox = f(0); r.oy = f(1); r.oz = f(2); r.dx = f(3); r.dy = f(4); r.dz = f(5); return r; }
+    SQT_HD void dfv(float &x, float &y, float &z) const { x = f(6); y = f(7); z = f(8); }
 };
 
 // ---- extension: analytic spheres (no reference counterpart; semantics restated in oracle/oracle.c) ----------------
@@ -269,46 +315,50 @@ SQT_HD bool ray_sphere(const float4 &s0, const Ray &r, float &t_out, float &dist
 
 // The BIH part of a ray is finished with `cur`: fold in the spheres (candidates in order [BIH hit, sphere 0, sphere 1, ..],
 // minimumBy (comparing dist): an earlier candidate wins ties), then the ray is ST_DONE.  Surface n_tris + k = sphere k.
-SQT_HD void finish_ray(const SceneView &sc, TravLane &L) {
-    for (uint32_t k = 0; k < sc.n_spheres; ++k) {
-        const float4 s0 = SQT_LDG4(sc.spheres + 2 * (size_t)k);
-        float t, dist;
-        if (ray_sphere(s0, L.r, t, dist)) {
-            if (L.cur.tri < 0 || cmp_gt(L.cur.dist, dist)) { L.cur.tri = (int)(sc.n_tris + k); L.cur.t = t; L.cur.dist = dist; }
+template <class RA>
+SQT_HD void finish_ray(const SceneView &sc, TravLane &L, const RA &ra) {
+    if (sc.n_spheres) {
+        const Ray r = ra.ray();
+        for (uint32_t k = 0; k < sc.n_spheres; ++k) {
+            const float4 s0 = SQT_LDG4(sc.spheres + 2 * (size_t)k);
+            float t, dist;
+            if (ray_sphere(s0, r, t, dist)) {
+                if (L.cur.tri < 0 || cmp_gt(L.cur.dist, dist)) { L.cur.tri = (int)(sc.n_tris + k); L.cur.t = t; L.cur.dist = dist; }
+            }
         }
     }
     L.state = ST_DONE;
 }
 
-// material index and (un-normalised) geometric normal of surface `idx` at the hit point (hx,hy,hz)
+// material index of surface `idx` (triangle in leaf order, or n_tris + sphere)
 SQT_HD uint32_t surface_material(const SceneView &sc, int idx) {
     if ((uint32_t)idx >= sc.n_tris) return f2u(SQT_LDG4(sc.spheres + 2 * (size_t)((uint32_t)idx - sc.n_tris) + 1).x);
     return f2u(SQT_LDG4(sc.tris + 3 * (size_t)idx + 2).y);
 }
 
-// intersectBIH b = intersectBIH' (bounds b) (tree b)   (BIH.hs:101-102)
+// intersectBIH b = intersectBIH' (bounds b) (tree b)   (BIH.hs:101-102).  Expects L.r; fills df, safe, sgn.
 template <bool COUNT>
 SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
     if (COUNT) cn->rays += 1;
     L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
     L.sp = 0;
+    L.dfx = XRCP(L.r.dx); L.dfy = XRCP(L.r.dy); L.dfz = XRCP(L.r.dz);
+    L.safe = sc.planes_finite && finite_f(L.dfx) && finite_f(L.dfy) && finite_f(L.dfz) && finite_f(L.r.dx) && finite_f(L.r.dy) &&
+             finite_f(L.r.dz) && finite_f(L.r.ox) && finite_f(L.r.oy) && finite_f(L.r.oz);
+    L.sgn = (L.r.dx > 0.0f ? 1u : 0u) | (L.r.dy > 0.0f ? 2u : 0u) | (L.r.dz > 0.0f ? 4u : 0u);
+    L.tmin = 0.0f; L.tmax = 0.0f;
     if (sc.root_is_leaf) {                       // tree = Leaf: no box test at all (BIH.hs:105)
         L.child = 0u; L.i = (int)sc.n_tris - 1;
         if (COUNT) cn->tri_tests += sc.n_tris;
-        if (sc.n_tris) L.state = ST_LEAF; else finish_ray(sc, L);
+        if (sc.n_tris) L.state = ST_LEAF; else finish_ray(sc, L, LaneRay(L));
         return;
     }
-    L.dfx = XRCP(L.r.dx); L.dfy = XRCP(L.r.dy); L.dfz = XRCP(L.r.dz);
-    L.safe = finite_f(L.dfx) && finite_f(L.dfy) && finite_f(L.dfz) && finite_f(L.r.dx) && finite_f(L.r.dy) &&
-             finite_f(L.r.dz) && finite_f(L.r.ox) && finite_f(L.r.oy) && finite_f(L.r.oz);
-    if (!slab_exact(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], L.r, L.dfx,
-                    L.dfy, L.dfz)) { finish_ray(sc, L); return; }          // BIH.hs:112 at the root
-    L.sgn = (L.r.dx > 0.0f ? 1u : 0u) | (L.r.dy > 0.0f ? 2u : 0u) | (L.r.dz > 0.0f ? 4u : 0u);
-    { const float d1 = fabsf(L.r.dx) + fabsf(L.r.dy) + fabsf(L.r.dz); L.dfac = d1 * (1.0f + d1); }
-    L.child = 0u; L.meta = 0u; L.state = ST_DESC;
+    if (!slab_iv(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], L.r, L.dfx,
+                 L.dfy, L.dfz, L.safe, L.tmin, L.tmax)) { finish_ray(sc, L, LaneRay(L)); return; }          // BIH.hs:112 at the root
+    L.child = 0u; L.state = ST_DESC;
 }
 
-// Entering Leaf `L.child` (index into the leaf array) with `count` triangles (BIH.hs:105-109).
+// Entering Leaf `L.child` (index into the leaf array) (BIH.hs:105-109).
 //
 // Conservative leaf culling (not in the reference; exact by a forward error bound, derivation in DESIGN.md section 5).
 // A triangle test can only return Just if |a| >= 1e-4 and the computed u, v, u+v pass their guards and t > 1e-4
@@ -320,22 +370,27 @@ SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
 // no skipped triangle could have been accepted, so the traversal result is bit-identical (tests: culling on/off
 // agree on every ray; both agree with the oracle).  Rays with a zero/denormal/non-finite direction component
 // (`safe` false) are never culled.
-template <bool COUNT>
-SQT_HD void enter_step(const SceneView &sc, TravLane &L, Counters *cn) {
-    const uint32_t count = L.meta & kCountMask;
-    L.cur.tri = -1;
-    if (count == 0u) { L.state = ST_RET; return; }                        // empty leaf -> Nothing (BIH.hs:107)
+template <bool COUNT, class RA>
+SQT_HD void enter_step(const SceneView &sc, TravLane &L, const RA &ra, Counters *cn) {
     const float4 *lp = sc.leaves + 2 * (size_t)L.child;
     const float4 b0 = SQT_LDG4(lp), b1 = SQT_LDG4(lp + 1);
+    const uint32_t w = f2u(b1.w), first = w & kLeafFirstMask;
+    uint32_t count = w >> kLeafCountShift;
+    L.cur.tri = -1;
+    if (count == 0u) { L.state = ST_RET; return; }                        // empty leaf -> Nothing (BIH.hs:107)
     if (sc.leaf_cull && L.safe) {
+        const Ray r = ra.ray();
+        float dfx, dfy, dfz;
+        ra.dfv(dfx, dfy, dfz);
+        const float d1 = fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz), dfac = d1 * (1.0f + d1);
         const float E = b1.z;
-        const float s1 = fabsf(L.r.ox - 0.5f * (b0.x + b0.w)) + fabsf(L.r.oy - 0.5f * (b0.y + b1.x)) +
-                         fabsf(L.r.oz - 0.5f * (b0.z + b1.y)) + ((b0.w - b0.x) + (b1.x - b0.y) + (b1.y - b0.z));
+        const float s1 = fabsf(r.ox - 0.5f * (b0.x + b0.w)) + fabsf(r.oy - 0.5f * (b0.y + b1.x)) +
+                         fabsf(r.oz - 0.5f * (b0.z + b1.y)) + ((b0.w - b0.x) + (b1.x - b0.y) + (b1.y - b0.z));
         const float cmax = fmaxf(fmaxf(fmaxf(fabsf(b0.x), fabsf(b0.w)), fmaxf(fabsf(b0.y), fabsf(b1.x))), fmaxf(fabsf(b0.z), fabsf(b1.y)));
-        const float m = 0.03f * (s1 + E) * L.dfac * (E * E) + (1.0e-4f + 9.5367431640625e-7f * (cmax + s1));
-        const float lx = (b0.x - m - L.r.ox) * L.dfx, hx = (b0.w + m - L.r.ox) * L.dfx;
-        const float ly = (b0.y - m - L.r.oy) * L.dfy, hy = (b1.x + m - L.r.oy) * L.dfy;
-        const float lz = (b0.z - m - L.r.oz) * L.dfz, hz = (b1.y + m - L.r.oz) * L.dfz;
+        const float m = 0.03f * (s1 + E) * dfac * (E * E) + (1.0e-4f + 9.5367431640625e-7f * (cmax + s1));
+        const float lx = (b0.x - m - r.ox) * dfx, hx = (b0.w + m - r.ox) * dfx;
+        const float ly = (b0.y - m - r.oy) * dfy, hy = (b1.x + m - r.oy) * dfy;
+        const float lz = (b0.z - m - r.oz) * dfz, hz = (b1.y + m - r.oz) * dfz;
         const float tmin = SQT_FMAX(SQT_FMAX(SQT_FMIN(lx, hx), SQT_FMIN(ly, hy)), SQT_FMIN(lz, hz));
         const float tmax = SQT_FMIN(SQT_FMIN(SQT_FMAX(lx, hx), SQT_FMAX(ly, hy)), SQT_FMAX(lz, hz));
         // keep the leaf unless the ray clearly misses; a NaN (cannot happen for safe rays) keeps it too
@@ -345,42 +400,68 @@ SQT_HD void enter_step(const SceneView &sc, TravLane &L, Counters *cn) {
             return;
         }
     }
+    if (count == kLeafLong) count = f2u(SQT_LDG4(sc.tris + 3 * (size_t)first + 2).w);   // long leaf: count rides in its first triangle
     if (COUNT) cn->tri_tests += count;
-    L.child = f2u(b1.w);
+    L.child = first;
     L.i = (int)count - 1;
     L.state = ST_LEAF;
 }
 
-// Word w of the lane's stack.  PLANE = 8: a plain array (lane-private local memory).  PLANE > 8: the stacks of a group of
-// PLANE/8 rays are interleaved in 32-byte granules -- granule g of every ray of the group is contiguous -- so that the few
-// granules in use (a stack is usually < 8 words deep) of all rays share cache lines instead of each ray owning lines of its
-// own (k_paths_pool: the stacks of all resident pool slots then fit L2).
-template <int PLANE>
-SQT_HD uint32_t &stack_word(TravLane &L, int w) {
-    return L.stack[PLANE == 8 ? w : (w >> 3) * PLANE + (w & 7)];
-}
-
-template <bool COUNT, int PLANE = 8>
-SQT_HD void desc_step(const SceneView &sc, TravLane &L, Counters *cn) {
-    const float4 *np = sc.nodes + kNodeQuads * (size_t)L.child;
-    const float4 q0 = SQT_LDG4(np), q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2), q3 = SQT_LDG4(np + 3);
-    const uint32_t left = f2u(q3.x), right = f2u(q3.y), lmeta = f2u(q3.z), rmeta = f2u(q3.w);
-    const uint32_t ax = (lmeta >> kAxisShift) & 3u;
-    bool hit_l, hit_r;
-    slab_children(q0, q1, q2, L.r, L.dfx, L.dfy, L.dfz, L.safe, hit_l, hit_r);
-    if (COUNT) { cn->branch_visits += 1; cn->child_box_tests += 2; }
-    if (!(hit_l || hit_r)) { L.cur.tri = -1; L.state = ST_RET; return; }
+// Visit Branch L.child (BIH.hs:111-141 below the own-box test, which the parent already evaluated).
+//
+// Fast path (safe ray, node not kSlow).  Let t_lo[k], t_hi[k] be the six slab values of the node's box and
+// near[k] = min(t_lo[k], t_hi[k]), far[k] = max(..): L.tmin = max_k near[k], L.tmax = min_k far[k] (Geometry.hs:175-176;
+// without NaNs min/max are exact selections, so association does not matter).  The left box replaces hi[ax] by lmax,
+// the right box lo[ax] by rmin (BIH.hs:130-141).  x -> (x - o)*df is monotone under round-to-nearest, so with
+// lo[ax] <= lmax <= hi[ax] the value tl = (lmax - o)*df lies between t_lo[ax] and t_hi[ax]: for df > 0 the left box
+// keeps near[ax] and lowers far[ax] to tl, hence tmin(left) = L.tmin, tmax(left) = min(L.tmax, tl); the right box
+// raises near[ax] to tr and keeps far[ax]: tmin(right) = max(L.tmin, tr), tmax(right) = L.tmax.  For df < 0 left and
+// right swap roles.  In both cases the child the reference calls `near` (left iff dir[ax] > 0, BIH.hs:124-127) gets
+// (L.tmin, min(L.tmax, t_near_plane)) and the far child (max(L.tmin, t_far_plane), L.tmax) -- the same values (up to
+// the sign of a zero, which no comparison sees) intersectsBB computes from all six slabs, at 2 subtractions,
+// 2 multiplications, 2 min/max and 3 compares instead of 12 + 12 + 20 + 4.
+template <bool COUNT, int STRIDE = 1, class RA>
+SQT_HD void desc_step(const SceneView &sc, TravLane &L, const RA &ra, Counters *cn) {
+    const float4 q = SQT_LDG4(sc.nodes + (size_t)L.child);
+    const uint32_t lb = f2u(q.z), rb = f2u(q.w);
+    const int ax = (int)((lb >> kAxisShift) & 3u);
     const bool ltr = ((L.sgn >> ax) & 1u) != 0u;                            // BIH.hs:127
-    const bool both = hit_l && hit_r;
-    const bool go_left = both ? ltr : hit_l;                                // near child first (BIH.hs:124-126)
-    const uint32_t lm = lmeta & (kLeaf | kCountMask);
-    if (both) {                                 // phase A frame: ONE word, this branch; ret_step re-reads plane and far child from the node
-        stack_word<PLANE>(L, L.sp) = L.child;
+    if (COUNT) { cn->branch_visits += 1; cn->child_box_tests += 2; }
+    float n_min, n_max, f_min, f_max;                                       // intervals of the near / far child
+    bool hit_n, hit_f;
+    if (L.safe && !(lb & kSlow)) {
+        const float o = ra.o(ax), df = ra.df(ax);
+        const float tl = XMUL(XSUB(q.x, o), df), tr = XMUL(XSUB(q.y, o), df);
+        n_min = L.tmin; n_max = SQT_FMIN(L.tmax, ltr ? tl : tr);
+        f_min = SQT_FMAX(L.tmin, ltr ? tr : tl); f_max = L.tmax;
+        hit_n = n_max > 0.0f && n_min < n_max;
+        hit_f = f_max > 0.0f && f_min < f_max;
+    } else {
+        // literal path: both child boxes from the node's own box (BIH.hs:130-141), all six slabs each
+        const float4 c0 = SQT_LDG4(sc.boxes + 2 * (size_t)L.child), c1 = SQT_LDG4(sc.boxes + 2 * (size_t)L.child + 1);
+        const Ray r = ra.ray();
+        float dfx, dfy, dfz;
+        ra.dfv(dfx, dfy, dfz);
+        float l_min, l_max, r_min, r_max;
+        const bool hit_l = slab_iv(c0.x, c0.y, c0.z, ax == 0 ? q.x : c0.w, ax == 1 ? q.x : c1.x, ax == 2 ? q.x : c1.y, r, dfx, dfy, dfz, L.safe, l_min, l_max);
+        const bool hit_r = slab_iv(ax == 0 ? q.y : c0.x, ax == 1 ? q.y : c0.y, ax == 2 ? q.y : c0.z, c0.w, c1.x, c1.y, r, dfx, dfy, dfz, L.safe, r_min, r_max);
+        hit_n = ltr ? hit_l : hit_r; hit_f = ltr ? hit_r : hit_l;
+        n_min = ltr ? l_min : r_min; n_max = ltr ? l_max : r_max;
+        f_min = ltr ? r_min : l_min; f_max = ltr ? r_max : l_max;
+    }
+    if (!(hit_n || hit_f)) { L.cur.tri = -1; L.state = ST_RET; return; }
+    const uint32_t nref = (ltr ? lb : rb) & (kLeaf | kIdxMask), fref = (ltr ? rb : lb) & (kLeaf | kIdxMask);
+    if (hit_n && hit_f) {                       // phase A entry: the far child, its interval, the plane isClose compares with
+        float4 e;
+        e.x = u2f(fref | ((uint32_t)ax << kAxisShift)); e.y = f_min; e.z = f_max; e.w = ltr ? q.y : q.x;      // rmin : lmax
+        L.stack[(size_t)L.sp * STRIDE] = e;
         L.sp += 1;
     }
-    L.child = go_left ? left : right;
-    L.meta = go_left ? lm : rmeta;
-    if (L.meta & kLeaf) L.state = ST_ENTER;
+    const uint32_t ref = hit_n ? nref : fref;
+    L.tmin = hit_n ? n_min : f_min;
+    L.tmax = hit_n ? n_max : f_max;
+    L.child = ref & kIdxMask;
+    L.state = (ref & kLeaf) ? ST_ENTER : ST_DESC;
 }
 
 // One triangle of the leaf (BIH.hs:105-109): V.mapMaybe over the leaf's triangles, minimumBy (comparing dist).
@@ -393,60 +474,55 @@ SQT_HD TriData tri_load(const SceneView &sc, uint32_t idx) {
     TriData d; d.a0 = SQT_LDG4(p); d.a1 = SQT_LDG4(p + 1); d.a2 = SQT_LDG4(p + 2);
     return d;
 }
+// the fold step of minimumBy (comparing dist) for a candidate that comes EARLIER in the leaf than everything folded so far
+SQT_HD void fold_earlier(Hit &cur, int tri, float t, float dist) {
+    if (cur.tri < 0 || !cmp_gt(dist, cur.dist)) { cur.tri = tri; cur.t = t; cur.dist = dist; }
+}
 // test the already loaded triangle L.child + L.i and advance (split from the load so that callers can prefetch)
 template <bool COUNT>
-SQT_HD void tri_apply(TravLane &L, const TriData &d, Counters *cn) {
+SQT_HD void tri_apply(TravLane &L, const Ray &r, const TriData &d, Counters *cn) {
     const uint32_t idx = L.child + (uint32_t)L.i;
     float t, dist;
     int stage;
-    if (moller_trumbore(d.a0, d.a1, d.a2, L.r, t, dist, stage)) {
-        if (L.cur.tri < 0 || !cmp_gt(dist, L.cur.dist)) { L.cur.tri = (int)idx; L.cur.t = t; L.cur.dist = dist; }
-    }
+    if (moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage)) fold_earlier(L.cur, (int)idx, t, dist);
     if (COUNT) { cn->mt_pass_a += stage >= 1; cn->mt_pass_u += stage >= 2; cn->mt_pass_v += stage >= 3; cn->mt_accept += stage >= 4; }
     if (--L.i < 0) L.state = ST_RET;
 }
 template <bool COUNT>
 SQT_HD void tri_step(const SceneView &sc, TravLane &L, Counters *cn) {
     const TriData d = tri_load(sc, L.child + (uint32_t)L.i);
-    tri_apply<COUNT>(L, d, cn);
+    tri_apply<COUNT>(L, L.r, d, cn);
 }
-// A subtree returned `cur`: pop entries until one of them sends the lane into a far subtree (-> ST_DESC / ST_ENTER) or
-// the stack is empty (-> ST_DONE).  Two kinds of entry, told apart by kPhaseB in the top word:
-//   phase A, 1 word  : index of a branch whose NEAR subtree just returned (both children were hit);
-//   phase B, 3 words : (t, dist, tri | kPhaseB), the parked near hit of a branch whose FAR subtree just returned.
-// Keeping phase A at one word (instead of caching plane / far child / meta in the entry) cuts the stack traffic to a
-// third; the branch's node is re-read on the way back -- it was read on the way down and is normally still in L1/L2.
-template <int PLANE = 8>
-SQT_HD void ret_step(const SceneView &sc, TravLane &L) {
+// A subtree returned `cur`: pop entries until one of them sends the ray into a far subtree (-> ST_DESC / ST_ENTER) or
+// the stack is empty (-> ST_DONE).  Two kinds of entry, told apart by kPhaseB in word 0:
+//   phase A : the NEAR subtree of a both-children-hit branch just returned; the entry names the far child, its
+//             interval and the plane (rmin when leftToRight, else lmax) isClose compares the hit point with;
+//   phase B : (tri | kPhaseB, t, dist), the parked near hit of a branch whose FAR subtree just returned.
+template <int STRIDE = 1, class RA>
+SQT_HD void ret_step(const SceneView &sc, TravLane &L, const RA &ra) {
     for (;;) {
-        if (L.sp == 0) { finish_ray(sc, L); return; }
-        const uint32_t w = stack_word<PLANE>(L, L.sp - 1);
-        if (w & kPhaseB) {                                                  // far subtree returned: min' near far
-            const uint32_t w0 = stack_word<PLANE>(L, L.sp - 3), w1 = stack_word<PLANE>(L, L.sp - 2);
-            L.sp -= 3;
-            if (L.cur.tri < 0 || !cmp_gt(u2f(w1), L.cur.dist)) { L.cur.tri = (int)(w & ~kPhaseB); L.cur.dist = u2f(w1); L.cur.t = u2f(w0); }
+        if (L.sp == 0) { finish_ray(sc, L, ra); return; }
+        float4 &slot = L.stack[(size_t)(L.sp - 1) * STRIDE];
+        const float4 e = slot;
+        const uint32_t w = f2u(e.x);
+        if (w & kPhaseB) {                                                  // far subtree returned: min' near far, near wins ties
+            L.sp -= 1;
+            if (L.cur.tri < 0 || !cmp_gt(e.z, L.cur.dist)) { L.cur.tri = (int)(w & ~kPhaseB); L.cur.t = e.y; L.cur.dist = e.z; }
             continue;
         }
-        L.sp -= 1;
-        // near subtree of branch w returned
-        const float4 *np = sc.nodes + kNodeQuads * (size_t)w;
-        const float4 q3 = SQT_LDG4(np + 3);
-        const uint32_t lmeta = f2u(q3.z);
-        const int ax = (int)((lmeta >> kAxisShift) & 3u);
-        const bool ltr = ((L.sgn >> ax) & 1u) != 0u;                        // BIH.hs:127: the near child was left iff leftToRight
         if (L.cur.tri >= 0) {
-            const float4 q1 = SQT_LDG4(np + 1), q2 = SQT_LDG4(np + 2);
-            const float plane = ltr ? sel3(ax, q2.y, q2.z, q2.w) : sel3(ax, q1.z, q1.w, q2.x);      // rmin : lmax
-            const float p = XADD(sel3(ax, L.r.ox, L.r.oy, L.r.oz), XMUL(L.cur.t, sel3(ax, L.r.dx, L.r.dy, L.r.dz)));   // intersectPoint on ax
-            const bool close = ltr ? (p < plane) : (p > plane);             // BIH.hs:121-123
-            if (close) continue;
-            stack_word<PLANE>(L, L.sp) = f2u(L.cur.t); stack_word<PLANE>(L, L.sp + 1) = f2u(L.cur.dist);
-            stack_word<PLANE>(L, L.sp + 2) = (uint32_t)L.cur.tri | kPhaseB;
-            L.sp += 3;
-        }
-        L.child = ltr ? f2u(q3.y) : f2u(q3.x);
-        L.meta = ltr ? f2u(q3.w) : (lmeta & (kLeaf | kCountMask));
-        L.state = (L.meta & kLeaf) ? ST_ENTER : ST_DESC;
+            const int ax = (int)((w >> kAxisShift) & 3u);
+            const bool ltr = ((L.sgn >> ax) & 1u) != 0u;                    // BIH.hs:127: the near child was left iff leftToRight
+            const float p = XADD(ra.o(ax), XMUL(L.cur.t, ra.d(ax)));        // intersectPoint on ax
+            const bool close = ltr ? (p < e.w) : (p > e.w);                 // BIH.hs:121-123
+            if (close) { L.sp -= 1; continue; }
+            float4 b;                                                       // park the near hit in the same slot
+            b.x = u2f((uint32_t)L.cur.tri | kPhaseB); b.y = L.cur.t; b.z = L.cur.dist; b.w = 0.0f;
+            slot = b;
+        } else L.sp -= 1;
+        L.tmin = e.y; L.tmax = e.z;
+        L.child = w & kIdxMask;
+        L.state = (w & kLeaf) ? ST_ENTER : ST_DESC;
         return;
     }
 }
@@ -454,15 +530,16 @@ SQT_HD void ret_step(const SceneView &sc, TravLane &L) {
 // one lane alone, to completion (host emulation and the odd single ray)
 template <bool COUNT>
 SQT_HD Hit traverse(const SceneView &sc, const Ray &r, Counters *cn) {
-    uint32_t stack[kStackWords];
+    float4 stack[kStackEntries];
     TravLane L;
     L.stack = stack;
     L.r = r;
     start_ray<COUNT>(sc, L, cn);
+    const LaneRay ra(L);
     while (L.state != ST_DONE) {
-        if (L.state == ST_RET) ret_step(sc, L);
-        if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
-        if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, cn);
+        if (L.state == ST_RET) ret_step(sc, L, ra);
+        if (L.state == ST_DESC) desc_step<COUNT>(sc, L, ra, cn);
+        if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, ra, cn);
         if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, cn);
     }
     return L.cur;

@@ -1,0 +1,550 @@
+// sqt_kernels.cuh -- the sm_100a kernels of the squigly-trace B200 backend (included by sqt_backend.cu only).
+//
+//   k_intersect_batch  : one lane per ray, grid-stride; batched Scene.intersect (Geometry.hs:64 / BIH.hs:101)
+//   k_primary          : one lane per pixel; makeRay (Lib.hs:107-114) + closest hit, cached per pixel
+//   k_paths_pool       : the integrator: every warp owns a pool of 32*K rays in shared memory, keeps them in three
+//                        queues by the kind of step they need and serves one queue per round with all lanes (default)
+//   k_paths            : the integrator with one ray per lane and warp-synchronous phases (SQT_POOL=0)
+//   k_accumulate       : adds a round's samples to the per-pixel sums in sample order (Lib.hs:88)
+//   k_raycast          : --cast mode (Lib.hs:141-151)
+//   k_tonemap          : mean + rgbFloatToPixelRGB (Lib.hs:88-104)
+//   k_leaf_records, k_check_materials : scene upload (leaf records from the triangles; material index validation)
+//   k_fp32_peak, k_l2_read : roofline denominators measured on the device
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <type_traits>
+
+#include "sqt_paths.cuh"
+
+namespace cg = cooperative_groups;
+using namespace sqt;
+
+struct DeviceStats {
+    unsigned long long rays, samples, primary_reused;
+    unsigned long long branch_visits, child_box_tests, tri_tests, leaves_culled;
+    unsigned long long mt_pass_a, mt_pass_u, mt_pass_v, mt_accept;
+    unsigned long long n_hit;           // length of the pixel list k_primary builds
+    unsigned long long work_next[256];  // dynamic work counters of the path kernels, one per round
+};
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// every lane of the block must call this (full warps)
+__device__ __forceinline__ void flush_stats(DeviceStats *ds, const PathStats &st, const Counters &cn, bool count) {
+    unsigned long long r = warp_sum(st.rays), s = warp_sum(st.samples), p = warp_sum(st.primary_reused);
+    unsigned long long b = 0, c = 0, t = 0;
+    unsigned long long lc = 0, ga = 0, gu = 0, gv = 0, gt = 0;
+    if (count) {
+        b = warp_sum(cn.branch_visits); c = warp_sum(cn.child_box_tests); t = warp_sum(cn.tri_tests); lc = warp_sum(cn.leaves_culled);
+        ga = warp_sum(cn.mt_pass_a); gu = warp_sum(cn.mt_pass_u); gv = warp_sum(cn.mt_pass_v); gt = warp_sum(cn.mt_accept);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (r) atomicAdd(&ds->rays, r);
+        if (s) atomicAdd(&ds->samples, s);
+        if (p) atomicAdd(&ds->primary_reused, p);
+        if (count) { atomicAdd(&ds->branch_visits, b); atomicAdd(&ds->child_box_tests, c); atomicAdd(&ds->tri_tests, t); atomicAdd(&ds->leaves_culled, lc);
+            atomicAdd(&ds->mt_pass_a, ga); atomicAdd(&ds->mt_pass_u, gu); atomicAdd(&ds->mt_pass_v, gv); atomicAdd(&ds->mt_accept, gt); }
+    }
+}
+
+// Scheduling knobs of the warp-synchronous loop (runtime so that they can be tuned without rebuilding; they
+// change the order in which lanes get served, never a result):
+//   a_leave : leave the traversal phase once at most this many lanes still want a traversal step
+//   b_leave : leave the triangle phase once fewer than this many lanes still have triangles to test
+//             (0 = the warp-cooperative triangle phase below, which always runs to completion)
+//   c_min   : run the regeneration phase only when at least this many lanes are done (or nothing else can run)
+struct Tune { int a_leave, b_leave, c_min; };
+
+// Warp-cooperative triangle phase of the one-ray-per-lane kernels.  The lanes that wait in a leaf hold (first triangle,
+// triangles left); their remaining (ray, triangle) tests are laid out consecutively by an exclusive scan and executed 32 at
+// a time, one test per lane, whichever lane owns the ray: the owner of test p is found by a binary search over the scan
+// (shuffles), the ray comes from the owner by shuffle.  Accepted hits (about one test in seventy) are handed back
+// to the owner one after the other in test order, i.e. from the leaf's last triangle to its first, so every ray
+// sees exactly the sequence of min' applications of BIH.hs:105-109 (base-4.9 minimumBy = foldr1 min').
+// Moller-Trumbore is a pure function of (ray, triangle), so only the lane that evaluates it changes.
+template <bool COUNT>
+__device__ __forceinline__ void leaf_pairs(const SceneView &sc, TravLane &L, Counters *cn) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool in_leaf = L.state == ST_LEAF;
+    const int left = in_leaf ? L.i + 1 : 0;
+    const int cnt = left < 1024 ? left : 1024;            // a pathological leaf is worked off over several phases
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int start = incl - cnt;
+    const int total = __shfl_sync(FULL, incl, 31);
+    for (int base = 0; base < total; base += 32) {
+        const int pr = base + lane;
+        int own = 0;                                       // first lane whose inclusive scan exceeds pr
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const int v = __shfl_sync(FULL, incl, own + s - 1);
+            if (v <= pr) own += s;
+        }
+        Ray r;
+        r.ox = __shfl_sync(FULL, L.r.ox, own); r.oy = __shfl_sync(FULL, L.r.oy, own); r.oz = __shfl_sync(FULL, L.r.oz, own);
+        r.dx = __shfl_sync(FULL, L.r.dx, own); r.dy = __shfl_sync(FULL, L.r.dy, own); r.dz = __shfl_sync(FULL, L.r.dz, own);
+        const uint32_t first = __shfl_sync(FULL, L.child, own);
+        const int oi = __shfl_sync(FULL, L.i, own), os = __shfl_sync(FULL, start, own);
+        const uint32_t idx = first + (uint32_t)(oi - (pr - os));
+        bool hit = false;
+        float t = 0.0f, dist = 0.0f;
+        if (pr < total) {
+            const TriData d = tri_load(sc, idx);
+            int stage;
+            hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
+            if (COUNT) { cn->mt_pass_a += stage >= 1; cn->mt_pass_u += stage >= 2; cn->mt_pass_v += stage >= 3; cn->mt_accept += stage >= 4; }
+        }
+        unsigned hm = __ballot_sync(FULL, hit);
+        while (hm != 0u) {                                 // rare: hand each accepted hit to its owner, in test order
+            const int src = __ffs(hm) - 1;
+            hm &= hm - 1u;
+            const int o_s = __shfl_sync(FULL, own, src);
+            const float t_s = __shfl_sync(FULL, t, src), d_s = __shfl_sync(FULL, dist, src);
+            const uint32_t i_s = __shfl_sync(FULL, idx, src);
+            if (lane == o_s) fold_earlier(L.cur, (int)i_s, t_s, d_s);
+        }
+    }
+    if (in_leaf) {
+        L.i -= cnt;
+        if (L.i < 0) L.state = ST_RET;
+    }
+}
+
+// The persistent warp loop of the one-ray-per-lane kernels.  Every lane of the warp stays in it until all 32 have run
+// out of work.  A round is three phases, each a tight loop whose trip count is decided by a warp vote: regeneration
+// (consume the finished hit, shade, make the next ray), traversal steps (stack pops + one branch visit), triangle steps
+// (one Moller-Trumbore test).  The votes force the 32 lanes back together at every phase boundary; an ordinary
+// per-lane loop nest compiles to code where the lanes drift apart through the data-dependent traversal and
+// never reconverge (measured: 2.4 of 32 lanes active, profiles/r01_k_paths_v0_divergent.txt).
+template <class P, class = void> struct has_warp_regen : std::false_type {};
+template <class P> struct has_warp_regen<P, std::void_t<decltype(P::kWarpRegen)>> : std::true_type {};
+
+template <bool COUNT, class Policy>
+__device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Counters *cn, const Tune tn) {
+    const unsigned FULL = 0xffffffffu;
+    float4 stack[kStackEntries];
+    TravLane L;
+    L.stack = stack;
+    L.state = ST_DONE; L.sp = 0; L.i = 0; L.child = 0u; L.tmin = 0.0f; L.tmax = 0.0f; L.safe = true; L.sgn = 0u;
+    L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
+    L.dfx = L.dfy = L.dfz = 0.0f;
+    L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
+    const LaneRay ra(L);
+    for (;;) {
+        // ---- regeneration
+        const unsigned m_done = __ballot_sync(FULL, L.state == ST_DONE);
+        const unsigned m_busy = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET || L.state == ST_LEAF || L.state == ST_ENTER);
+        if (m_done != 0u && (__popc(m_done) >= tn.c_min || m_busy == 0u)) {
+            if constexpr (has_warp_regen<Policy>::value) pol.template regen_warp<COUNT>(sc, L, cn, L.state == ST_DONE);
+            else { if (L.state == ST_DONE) pol.template regen<COUNT>(sc, L, cn); }
+            __syncwarp(FULL);
+        } else if (m_busy == 0u) break;                       // every lane is ST_EXIT
+        // ---- traversal steps (stack pops + one branch visit) while more than a_leave lanes want one; then every
+        //      lane that found a leaf enters it (record fetch + conservative culling; culled lanes traverse on).
+        //      The few stragglers left over keep their state and continue next round.
+        for (;;) {
+            const unsigned mt = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET);
+            if (__popc(mt) > tn.a_leave) {
+                if (L.state == ST_RET) ret_step(sc, L, ra);
+                if (L.state == ST_DESC) desc_step<COUNT>(sc, L, ra, cn);
+                continue;
+            }
+            if (__any_sync(FULL, L.state == ST_ENTER)) {
+                if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, ra, cn);
+                continue;
+            }
+            if (mt != 0u && !__any_sync(FULL, L.state == ST_LEAF)) {      // only stragglers are left and nobody has triangles
+                if (L.state == ST_RET) ret_step(sc, L, ra);
+                if (L.state == ST_DESC) desc_step<COUNT>(sc, L, ra, cn);
+                continue;
+            }
+            break;
+        }
+        // ---- triangle tests: all lanes share the tests of the lanes that wait in a leaf, or one test per lane and step
+        unsigned m = __ballot_sync(FULL, L.state == ST_LEAF);
+        if (tn.b_leave == 0) {
+            if (m != 0u) leaf_pairs<COUNT>(sc, L, cn);
+            continue;
+        }
+        while (m != 0u) {
+            if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, cn);
+            m = __ballot_sync(FULL, L.state == ST_LEAF);
+            if (__popc(m) < tn.b_leave) break;
+        }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_intersect_batch(SceneView sc, const float *__restrict__ org,
+                                                         const float *__restrict__ dir, long long n,
+                                                         int *__restrict__ tri_out, float *__restrict__ dist_out,
+                                                         float *__restrict__ point_out, DeviceStats *ds, Tune tn) {
+    Counters cn = {};
+    PathStats st = {0, 0, 0};
+    BatchPolicy pol(org, dir, n, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, tri_out,
+                    dist_out, point_out, st);
+    warp_loop<COUNT>(sc, pol, &cn, tn);
+    flush_stats(ds, st, cn, COUNT);
+}
+
+struct DeviceAppend {
+    unsigned long long *counter;
+    int *list;
+    __device__ __forceinline__ void operator()(long long pixel) {
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned long long base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(counter, (unsigned long long)g.size());
+        base = g.shfl(base, 0);
+        list[base + g.thread_rank()] = (int)pixel;
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_primary(SceneView sc, RenderParams p, int2 *__restrict__ prim, int *__restrict__ pixel_list,
+                                                 DeviceStats *ds, Tune tn) {
+    Counters cn = {};
+    PathStats st = {0, 0, 0};
+    DeviceAppend app = {&ds->n_hit, pixel_list};
+    PrimaryPolicy<DeviceAppend> pol(p, prim, app, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                                    (long long)gridDim.x * blockDim.x, st);
+    warp_loop<COUNT>(sc, pol, &cn, tn);
+    flush_stats(ds, st, cn, COUNT);
+}
+
+struct DeviceFetch {
+    unsigned long long *counter;
+    long long n;
+    __device__ __forceinline__ long long operator()() {
+        // warp-aggregated claim: one atomic per group of lanes that need work at the same time
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned long long base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(counter, (unsigned long long)g.size());
+        base = g.shfl(base, 0);
+        const long long w = (long long)(base + g.thread_rank());
+        return w < n ? w : -1;
+    }
+};
+
+#ifndef SQT_WL_MIN_BLOCKS
+#define SQT_WL_MIN_BLOCKS 6
+#endif
+// One round of samples (sqt_paths.cuh): persistent lanes pull (pixel, sample) items from the round's counter.
+template <bool COUNT>
+__global__ void __launch_bounds__(128, SQT_WL_MIN_BLOCKS) k_paths(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, Tune tn) {
+    Counters cn = {};
+    PathStats st = {0, 0, 0};
+    if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
+    DeviceFetch fetch = {&ds->work_next[round], rd.n_slots << rd.log2_s};
+    uint16_t pm[SQT_MAX_DEPTH];
+    PathPolicy<DeviceFetch> pol(p, rd, fetch, st, pm);
+    warp_loop<COUNT>(sc, pol, &cn, tn);
+    flush_stats(ds, st, cn, COUNT);
+}
+
+// ------------------------------------------------------------------------------ ray pools
+// k_paths_pool: the same per-ray logic as k_paths, scheduled differently.  Every warp owns a POOL of P = 32*K rays whose
+// state lives in shared memory (structure of arrays, 16 words per ray; traversal stacks, per-path material lists and the
+// integrator state of a slot in global memory, one region per pool slot).  A ray waits in one of three queues (rings of
+// slot ids in shared memory, appended to with a ballot + popc at write-back, so there is no census and no gather):
+//   T  traversal steps (ST_DESC / ST_RET): a short burst of branch visits + stack pops; the ray's interval, child and best
+//      hit travel in registers, its origin / direction components are read from the pool by split axis (PoolRay)
+//   L  leaf work (ST_ENTER / ST_LEAF): every gathered ray enters its leaf (record fetch + conservative culling), then the
+//      (ray, triangle) tests of ALL gathered rays are laid out consecutively and executed 32 per step, one test per lane,
+//      whichever lane gathered the ray -- any lane can read any ray from the pool -- and accepted hits are folded into
+//      the owning ray's best hit in test order (from the leaf's last triangle to its first: BIH.hs:105-109, minimumBy =
+//      foldr1 min'); leaves are always worked off to completion, so a ray leaves this queue as ST_RET
+//   R  regeneration (ST_DONE): consume the hit, shade, bounce or fetch the next sample, start the ray (staged for all
+//      gathered lanes at once, path_regen_warp)
+// Each round the warp serves the longest queue with up to 32 lanes.  With one ray per lane at most ~10 of 32 lanes share a
+// step kind at any time (tests/sched_sim.py); regrouping rays lifts that limit.  Scheduling never changes a result: every
+// ray runs the same unit steps of sqt_core.cuh in the same order (test_every_path_kernel_scheduler_is_bit_exact).
+#ifndef SQT_POOL_MIN_BLOCKS
+#define SQT_POOL_MIN_BLOCKS 9
+#endif
+// burst_t: traversal steps per T round (at most); t_leave: end the burst early once at most this many lanes still traverse;
+// c_min: serve the regeneration queue only when it holds at least this many rays (or nothing else can run)
+struct PoolTune { int burst_t, t_leave, c_min; };
+
+// 16 words = 64 B per ray in shared memory; the first nine are what PoolRay reads.  PF_TMIN holds the interval's lower
+// end while the ray descends and `i` (triangles left - 1) for a ray that starts inside a leaf (root leaf);
+// PF_FLAGS = state | safe << 8 | sgn << 16 | sp << 24.
+enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_TMIN, PF_TMAX, PF_CTRI, PF_CT, PF_CDIST,
+       PF_FLAGS, PF_WORDS };
+enum { KT = 0, KL = 1, KR = 2, KNONE = 3 };
+
+template <bool COUNT, int K>
+__global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, PoolTune tn,
+                                                    float4 *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath, int stack_depth, int pm_stride) {
+    extern __shared__ uint32_t pool_smem[];
+    constexpr int P = 32 * K;
+    constexpr int WARP_WORDS = P * PF_WORDS + 3 * (P / 4);
+    const unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *pool = pool_smem + warp * WARP_WORDS;
+    uint8_t *queue = (uint8_t *)(pool + P * PF_WORDS);                          // queue[k * P + i], k = KT, KL, KR
+    const int gslot0 = (int)((blockIdx.x * (blockDim.x >> 5) + warp) * P);     // < 2^31: at most a few hundred thousand pool slots exist
+    float4 *wstack = gstack + (size_t)gslot0 * (size_t)stack_depth;            // entry e of slot s at wstack[e * P + s]
+#define PW(f, slot) pool[(f) * P + (slot)]
+    Counters cn = {};
+    PathStats st = {0, 0, 0};
+    if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
+    DeviceFetch fetch = {&ds->work_next[round], rd.n_slots << rd.log2_s};
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int slot = lane + 32 * k;
+        PW(PF_FLAGS, slot) = (uint32_t)ST_DONE;
+        PW(PF_CTRI, slot) = 0xffffffffu;
+        queue[KR * P + slot] = (uint8_t)slot;
+        gpath[2 * (gslot0 + slot)] = make_uint4(0u, 0u, 0u, 0u);
+        gpath[2 * (gslot0 + slot) + 1] = make_uint4(0u, 0u, 0u, 0u);      // saved_j = -1 (stored +1), any_emit = in_flight = false
+    }
+    __syncwarp(FULL);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int q_head[3] = {0, 0, 0}, q_cnt[3] = {0, 0, P};                       // warp-uniform
+    for (;;) {
+        // ---- pick the longest queue (regeneration only in batches, or when nothing else can run)
+        const int c_r = (q_cnt[KR] >= tn.c_min || (q_cnt[KT] | q_cnt[KL]) == 0) ? q_cnt[KR] : 0;
+        int kind = KL, best = q_cnt[KL];
+        if (q_cnt[KT] > best) { kind = KT; best = q_cnt[KT]; }
+        if (c_r > best) { kind = KR; best = c_r; }
+        if (best == 0) break;                                               // every slot is ST_EXIT
+        // ---- pop up to 32 rays of that kind onto the lanes
+        const int n_sel = best < 32 ? best : 32;
+        const bool act = lane < n_sel;
+        int slot = 0;
+        {
+            const int h = kind == KT ? q_head[KT] : (kind == KL ? q_head[KL] : q_head[KR]);
+            int pos = h + lane;
+            if (pos >= P) pos -= P;
+            if (act) slot = (int)queue[kind * P + pos];
+            int nh = h + n_sel;
+            if (nh >= P) nh -= P;
+            if (kind == KT) { q_head[KT] = nh; q_cnt[KT] -= n_sel; }
+            else if (kind == KL) { q_head[KL] = nh; q_cnt[KL] -= n_sel; }
+            else { q_head[KR] = nh; q_cnt[KR] -= n_sel; }
+        }
+        TravLane L;
+        L.stack = nullptr;
+        L.state = ST_EXIT;
+        const PoolRay ra(pool + slot, P);
+        if (kind == KT) {
+            // ---- traversal steps: stack pops + branch visits
+            uint32_t fl = 0u;
+            L.stack = wstack + slot;
+            if (act) {
+                L.child = PW(PF_CHILD, slot); L.tmin = u2f(PW(PF_TMIN, slot)); L.tmax = u2f(PW(PF_TMAX, slot));
+                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
+                fl = PW(PF_FLAGS, slot);
+                L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
+            }
+            for (int b = 0; b < tn.burst_t; ++b) {
+                if (L.state == ST_RET) ret_step<P>(sc, L, ra);
+                if (L.state == ST_DESC) desc_step<COUNT, P>(sc, L, ra, &cn);
+                if (__popc(__ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET)) <= tn.t_leave) break;
+            }
+            if (act) {
+                PW(PF_CHILD, slot) = L.child; PW(PF_TMIN, slot) = f2u(L.tmin); PW(PF_TMAX, slot) = f2u(L.tmax);
+                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
+                PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
+            }
+        } else if (kind == KL) {
+            // ---- leaf work.  Stage 1: enter the leaf (record fetch + conservative culling)
+            uint32_t fl = 0u;
+            uint32_t first = 0u;
+            int rem = 0;                                                    // triangles of this lane's ray still to test
+            if (act) {
+                fl = PW(PF_FLAGS, slot);
+                L.child = PW(PF_CHILD, slot);
+                L.safe = ((fl >> 8) & 1u) != 0u;
+                L.state = (int)(fl & 0xffu);
+                L.i = (int)PW(PF_TMIN, slot);                               // only meaningful for a ray that started inside a (root) leaf
+                L.cur.tri = (int)PW(PF_CTRI, slot);
+                if (L.state == ST_ENTER) {
+                    enter_step<COUNT>(sc, L, ra, &cn);
+                    PW(PF_CTRI, slot) = 0xffffffffu;                        // enter_step: cur = Nothing
+                }
+                if (L.state == ST_LEAF) { first = L.child; rem = L.i + 1; }
+            }
+            __syncwarp(FULL);
+            // Stage 2: all (ray, triangle) tests of the gathered rays, 32 per step.  Test p of a pass belongs to the lane
+            // whose inclusive scan first exceeds p; within a ray tests run from its last triangle to its first.
+            for (;;) {
+                const int c = rem < 1024 ? rem : 1024;                     // a pathological leaf is worked off over several passes
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                if (total == 0) break;
+                const int tri_base = (int)first + rem - 1 + (incl - c);     // triangle of test p (of this lane's ray) = tri_base - p
+                for (int base = 0; base < total; base += 32) {
+                    const int pr = base + lane;
+                    int own = 0;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) {
+                        const int v = __shfl_sync(FULL, incl, own + s - 1);
+                        if (v <= pr) own += s;
+                    }
+                    const int oslot = __shfl_sync(FULL, slot, own);
+                    const uint32_t idx = (uint32_t)(__shfl_sync(FULL, tri_base, own) - pr);
+                    bool hit = false;
+                    float t = 0.0f, dist = 0.0f;
+                    if (pr < total) {
+                        const TriData d = tri_load(sc, idx);
+                        const Ray r = PoolRay(pool + oslot, P).ray();
+                        int stage;
+                        hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
+                        if (COUNT) { cn.mt_pass_a += stage >= 1; cn.mt_pass_u += stage >= 2; cn.mt_pass_v += stage >= 3; cn.mt_accept += stage >= 4; }
+                    }
+                    unsigned hm = __ballot_sync(FULL, hit);
+                    while (hm != 0u) {                                      // rare: fold each accepted hit into its ray, in test order
+                        const int src = __ffs(hm) - 1;
+                        hm &= hm - 1u;
+                        if (lane == src) {                                  // fold_earlier on the ray's best hit in the pool
+                            if ((int)PW(PF_CTRI, oslot) < 0 || !cmp_gt(dist, u2f(PW(PF_CDIST, oslot)))) {
+                                PW(PF_CTRI, oslot) = idx; PW(PF_CT, oslot) = f2u(t); PW(PF_CDIST, oslot) = f2u(dist);
+                            }
+                        }
+                        __syncwarp(FULL);
+                    }
+                }
+                rem -= c;
+            }
+            if (act) { L.state = ST_RET; PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)ST_RET; }
+        } else {
+            // ---- regeneration: consume the finished hit, shade, start the next ray (or the next sample); staged, all
+            //      gathered lanes together (path_regen_warp)
+            PathRay q;
+            path_ray_init(q);
+            uint4 *gp = gpath + 2 * (gslot0 + slot);
+            L.dfx = L.dfy = L.dfz = 0.0f; L.child = 0u; L.tmin = 0.0f; L.tmax = 0.0f; L.i = 0; L.sp = 0; L.safe = true; L.sgn = 0u;
+            L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
+            L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
+            if (act) {
+                L.r.ox = u2f(PW(PF_OX, slot)); L.r.oy = u2f(PW(PF_OY, slot)); L.r.oz = u2f(PW(PF_OZ, slot));
+                L.r.dx = u2f(PW(PF_DX, slot)); L.r.dy = u2f(PW(PF_DY, slot)); L.r.dz = u2f(PW(PF_DZ, slot));
+                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
+                L.state = ST_DONE;
+                const uint4 g0 = gp[0], g1 = gp[1];
+                const uint32_t pf = g1.y;
+                q.sidx = g0.x; q.j = (int)g0.y;
+                q.stream = (unsigned long long)g0.z | ((unsigned long long)g0.w << 32);
+                q.saved_r = u2f(g1.x); q.saved_j = (int)(pf & 0xffffu) - 1;
+                q.any_emit = ((pf >> 16) & 1u) != 0u; q.in_flight = ((pf >> 17) & 1u) != 0u;
+            }
+            path_regen_warp<COUNT>(sc, p, rd, fetch, st, q, gpm + (size_t)(gslot0 + slot) * (size_t)pm_stride, L, &cn, act);
+            if (act) {
+                PW(PF_OX, slot) = f2u(L.r.ox); PW(PF_OY, slot) = f2u(L.r.oy); PW(PF_OZ, slot) = f2u(L.r.oz);
+                PW(PF_DX, slot) = f2u(L.r.dx); PW(PF_DY, slot) = f2u(L.r.dy); PW(PF_DZ, slot) = f2u(L.r.dz);
+                PW(PF_DFX, slot) = f2u(L.dfx); PW(PF_DFY, slot) = f2u(L.dfy); PW(PF_DFZ, slot) = f2u(L.dfz);
+                PW(PF_CHILD, slot) = L.child; PW(PF_TMIN, slot) = L.state == ST_LEAF ? (uint32_t)L.i : f2u(L.tmin); PW(PF_TMAX, slot) = f2u(L.tmax);
+                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
+                PW(PF_FLAGS, slot) = (uint32_t)L.state | (L.safe ? 0x100u : 0u) | (L.sgn << 16) | ((uint32_t)L.sp << 24);
+                gp[0] = make_uint4(q.sidx, (uint32_t)q.j, (uint32_t)q.stream, (uint32_t)(q.stream >> 32));
+                gp[1] = make_uint4(f2u(q.saved_r), (uint32_t)(q.saved_j + 1) | (q.any_emit ? 0x10000u : 0u) | (q.in_flight ? 0x20000u : 0u), 0u, 0u);
+            }
+        }
+        // ---- append every served ray to the queue of the step it needs next
+        {
+            // ST_DONE 0 -> KR, ST_DESC 1 -> KT, ST_LEAF 2 -> KL, ST_RET 3 -> KT, ST_EXIT 4 -> none, ST_ENTER 5 -> KL
+            const int nk = act ? (int)((0x130102u >> (4 * L.state)) & 3u) : KNONE;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const unsigned m = __ballot_sync(FULL, nk == k);
+                if (nk == k) {
+                    int pos = q_head[k] + q_cnt[k] + __popc(m & lt_mask);
+                    if (pos >= P) pos -= P;
+                    queue[k * P + pos] = (uint8_t)slot;
+                }
+                q_cnt[k] += __popc(m);
+            }
+        }
+        __syncwarp(FULL);
+    }
+#undef PW
+    flush_stats(ds, st, cn, COUNT);
+}
+
+// sum the round's samples into the per-pixel running sums, in sample order (Lib.hs:88)
+__global__ void __launch_bounds__(256) k_accumulate(RenderParams p, RoundInfo rd, float *__restrict__ accum, const DeviceStats *ds) {
+    if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < rd.n_slots; slot += stride)
+        accumulate_slot(p, rd, slot, accum);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_raycast(SceneView sc, RenderParams p, float *__restrict__ accum, DeviceStats *ds, Tune tn) {
+    Counters cn = {};
+    PathStats st = {0, 0, 0};
+    CastPolicy pol(p, accum, work_items(p), (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, st);
+    warp_loop<COUNT>(sc, pol, &cn, tn);
+    flush_stats(ds, st, cn, COUNT);
+}
+
+// avg = (1 / fromIntegral sampleCount) *^ sum outcomes ; rgbFloatToPixelRGB avg   (Lib.hs:88-89)
+__global__ void __launch_bounds__(256) k_tonemap(const float *__restrict__ accum, long long npix, float inv_spp,
+                                                 uint8_t *__restrict__ rgb8) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    uint8_t o[3];
+    tone_map(XMUL(inv_spp, accum[3 * i]), XMUL(inv_spp, accum[3 * i + 1]), XMUL(inv_spp, accum[3 * i + 2]), o);
+    rgb8[3 * i] = o[0]; rgb8[3 * i + 1] = o[1]; rgb8[3 * i + 2] = o[2];
+}
+
+// scene upload: the leaf records (tight box, longest edge, range) from the triangles of every leaf, and the
+// material-index check, on the device -- 10 M triangles take a millisecond here and half a second on one host core
+__global__ void __launch_bounds__(256) k_leaf_records(float4 *tris, const uint2 *__restrict__ ranges, uint32_t n_leaves, float4 *__restrict__ leaves) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_leaves) return;
+    const uint2 r = ranges[i];
+    float4 b0, b1;
+    make_leaf_record(tris, r.x, r.y, b0, b1);
+    leaves[2 * (size_t)i] = b0; leaves[2 * (size_t)i + 1] = b1;
+    if (r.y >= kLeafLong) tris[3 * (size_t)r.x + 2].w = __uint_as_float(r.y);
+}
+__global__ void __launch_bounds__(256) k_check_materials(const float4 *__restrict__ tris, uint32_t n_tris, uint32_t n_mats, uint32_t *bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tris && __float_as_uint(tris[3 * (size_t)i + 2].y) >= n_mats) atomicMin(bad, i);
+}
+
+// Non-fused FP32 issue rate: 16 independent chains per lane, alternating FMUL / FADD (the op mix of the
+// bit-exact intersection path, where FMA contraction is forbidden).
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float a, float b) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) { x[i] = __fmul_rn(x[i], a); x[i + 1] = __fadd_rn(x[i + 1], b); }
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) { x[i] = __fadd_rn(x[i], b); x[i + 1] = __fmul_rn(x[i + 1], a); }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 123.456f) out[0] = s;      // keep the chains alive
+}
+
+// L2-resident 128-bit read bandwidth: every block sweeps the same `n4`-element buffer `reps` times.
+__global__ void __launch_bounds__(256) k_l2_read(const float4 *__restrict__ buf, long long n4, int reps, float *out) {
+    float s = 0.0f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int r = 0; r < reps; ++r)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            float4 v;
+            asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(buf + i));
+            s += v.x + v.y + v.z + v.w;
+        }
+    if (s == 123.456f) out[0] = s;
+}

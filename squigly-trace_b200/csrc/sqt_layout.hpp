@@ -1,10 +1,11 @@
 // sqt_layout.hpp -- host-side derivation of the device records from the C-ABI scene description.
 //
-// Walks the boundary tree once (iteratively), validating it and deriving for every Branch the box
-// intersectBIH' would receive for it: the root gets `bounds`, a left child gets its parent's box with
+// Walks the boundary tree once (iteratively), validating it and deriving for every Branch its 16-byte device node and
+// the box intersectBIH' would receive for it: the root gets `bounds`, a left child gets its parent's box with
 // hi[axis] := lmax, a right child the parent's box with lo[axis] := rmin (BIH.hs:130-141).  Plane values
-// are copied, never computed.  Shared by sqt_backend.cu (the product) and tests/emu (host build of the
-// kernel logic).
+// are copied, never computed.  The leaf records and the material-index check are per-triangle work and are left to the
+// caller (device kernels in the product, make_leaf_record on the host in tests/emu).  Shared by sqt_backend.cu (the
+// product) and tests/emu (host build of the kernel logic).
 #pragma once
 #include <cmath>
 #include <cstdarg>
@@ -18,10 +19,13 @@
 namespace sqt {
 
 struct DeviceLayout {
-    std::vector<float4> nodes;      // kNodeQuads per branch
+    std::vector<float4> nodes;      // 1 per branch: (lmax, rmin, L, R)
+    std::vector<float4> boxes;      // 2 per branch: the clipped box intersectBIH' receives for it (slow path only)
     std::vector<float4> mats;       // 3 per material
-    std::vector<float4> leaves;     // 2 per leaf (leaf order = order of first appearance in the node array)
-    uint32_t n_branches = 0, height = 0;
+    std::vector<uint32_t> leaf_first, leaf_count;   // triangle range per leaf (leaf order = order of first appearance in the node
+                                                    // array); the leaf RECORDS are derived from the triangles by make_leaf_record
+    uint32_t n_branches = 0, n_slow = 0, height = 0;
+    int planes_finite = 1;
     int terminate_on_black_ok = 0;
 };
 
@@ -33,13 +37,13 @@ inline int layout_fail(std::string &err, int code, const char *fmt, ...) {
 }
 inline float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
-inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, std::string &err) {
+inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, std::string &err, bool check_materials = true) {
     const sqt_scene_desc *s = &desc;
     if (!s->nodes || s->n_nodes == 0) return layout_fail(err, SQT_E_INVALID, "scene has no BIH nodes");
     if (s->n_tris && !s->tris) return layout_fail(err, SQT_E_INVALID, "tris is NULL");
     if (!s->mats || s->n_mats == 0) return layout_fail(err, SQT_E_INVALID, "scene has no materials");
     if (s->n_mats > 65535) return layout_fail(err, SQT_E_UNSUPPORTED, "more than 65535 materials");
-    if (s->n_tris >= (1u << 27) || s->n_nodes >= (1u << 30)) return layout_fail(err, SQT_E_UNSUPPORTED, "scene too large for the 27/30-bit indices");
+    if (s->n_tris >= (1u << 27) || s->n_nodes >= (1u << 28)) return layout_fail(err, SQT_E_UNSUPPORTED, "scene too large for the 27/28-bit indices");
     const uint32_t N = s->n_nodes;
     std::vector<int32_t> branch_id(N, -1), leaf_id(N, -1);
     uint32_t n_br = 0, n_lf = 0;
@@ -47,24 +51,27 @@ inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, st
         if (!(s->nodes[i].b & SQT_NODE_LEAF)) branch_id[i] = (int32_t)n_br++;
         else leaf_id[i] = (int32_t)n_lf++;
     }
-    std::vector<float4> dl((size_t)2 * (n_lf ? n_lf : 1));
+    out.leaf_first.assign(n_lf ? n_lf : 1, 0u); out.leaf_count.assign(n_lf ? n_lf : 1, 0u);
     struct Box { float lo[3], hi[3]; };
-    std::vector<float4> dn((size_t)kNodeQuads * (n_br ? n_br : 1));
+    std::vector<float4> dn((size_t)(n_br ? n_br : 1)), db((size_t)2 * (n_br ? n_br : 1));
     std::vector<uint8_t> seen(N, 0);
-    std::vector<uint8_t> tri_cover(s->n_tris ? s->n_tris : 1, 0);
     struct Item { uint32_t node; Box box; uint32_t depth; };
     std::vector<Item> todo;
     Box root;
-    for (int k = 0; k < 3; ++k) { root.lo[k] = s->root_bounds[k]; root.hi[k] = s->root_bounds[3 + k]; }
+    int planes_finite = 1;
+    for (int k = 0; k < 3; ++k) {
+        root.lo[k] = s->root_bounds[k]; root.hi[k] = s->root_bounds[3 + k];
+        if (!std::isfinite(root.lo[k]) || !std::isfinite(root.hi[k])) planes_finite = 0;
+    }
     todo.push_back({0u, root, 1u});
-    uint32_t height = 0;
-    auto leaf_meta = [&](uint32_t child, uint32_t &ref, uint32_t &meta) -> const char * {
+    uint32_t height = 0, n_slow = 0;
+    auto child_ref = [&](uint32_t child, uint32_t &ref) -> const char * {
         const sqt_node &c = s->nodes[child];
         if (c.b & SQT_NODE_LEAF) {
             const uint32_t cnt = c.b & ~SQT_NODE_LEAF, first = c.a;
             if ((uint64_t)first + cnt > s->n_tris) return "leaf triangle range out of bounds";
-            ref = (uint32_t)leaf_id[child]; meta = kLeaf | cnt;
-        } else { ref = (uint32_t)branch_id[child]; meta = 0; }
+            ref = (uint32_t)leaf_id[child] | kLeaf;
+        } else ref = (uint32_t)branch_id[child];
         return nullptr;
     };
     while (!todo.empty()) {
@@ -77,48 +84,33 @@ inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, st
         if (nd.b & SQT_NODE_LEAF) {
             const uint32_t cnt = nd.b & ~SQT_NODE_LEAF;
             if ((uint64_t)nd.a + cnt > s->n_tris) return layout_fail(err, SQT_E_INVALID, "leaf %u: triangle range out of bounds", it.node);
-            // tight box of the triangles as Moller-Trumbore sees them (v0, v0+e1, v0+e2) and their longest edge
-            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, e2max = 0;
-            for (uint32_t t = 0; t < cnt; ++t) {
-                tri_cover[nd.a + t] = 1;
-                const sqt_tri &tr = s->tris[nd.a + t];
-                double l1 = 0, l2 = 0, l3 = 0;
-                for (int k = 0; k < 3; ++k) {
-                    const double v[3] = {(double)tr.v0[k], (double)tr.v0[k] + tr.e1[k], (double)tr.v0[k] + tr.e2[k]};
-                    for (double x : v) { if (x < lo[k]) lo[k] = x; if (x > hi[k]) hi[k] = x; }
-                    l1 += (double)tr.e1[k] * tr.e1[k]; l2 += (double)tr.e2[k] * tr.e2[k];
-                    l3 += ((double)tr.e2[k] - tr.e1[k]) * ((double)tr.e2[k] - tr.e1[k]);
-                }
-                e2max = std::fmax(e2max, std::fmax(l1, std::fmax(l2, l3)));
-            }
-            if (cnt == 0) { for (int k = 0; k < 3; ++k) lo[k] = hi[k] = 0; }
-            auto dn_ = [](double x) { return std::nextafterf((float)x, -INFINITY); };     // round outwards
-            auto up_ = [](double x) { return std::nextafterf((float)x, INFINITY); };
-            const size_t q = (size_t)2 * (size_t)leaf_id[it.node];
-            dl[q] = mk4(dn_(lo[0]), dn_(lo[1]), dn_(lo[2]), up_(hi[0]));
-            dl[q + 1] = mk4(up_(hi[1]), up_(hi[2]), up_(std::sqrt(e2max)), u2f(nd.a));
+            out.leaf_first[(size_t)leaf_id[it.node]] = cnt ? nd.a : 0u; out.leaf_count[(size_t)leaf_id[it.node]] = cnt;
             continue;
         }
         const uint32_t ax = nd.a >> 30, l = nd.a & 0x3fffffffu, r = nd.b;
         if (ax > 2) return layout_fail(err, SQT_E_INVALID, "node %u: axis %u", it.node, ax);
         if (l >= N || r >= N) return layout_fail(err, SQT_E_INVALID, "node %u: child out of range", it.node);
-        uint32_t lref = 0, lmeta = 0, rref = 0, rmeta = 0;
-        const char *e1 = leaf_meta(l, lref, lmeta), *e2 = leaf_meta(r, rref, rmeta);
+        uint32_t lref = 0, rref = 0;
+        const char *e1 = child_ref(l, lref), *e2 = child_ref(r, rref);
         if (e1 || e2) return layout_fail(err, SQT_E_INVALID, "node %u: %s", it.node, e1 ? e1 : e2);
-        lmeta |= ax << kAxisShift;
         Box lb = it.box, rb = it.box;
         lb.hi[ax] = nd.lmax; rb.lo[ax] = nd.rmin;                           // BIH.hs:130-141
-        const size_t b = (size_t)kNodeQuads * (size_t)branch_id[it.node];
-        dn[b] = mk4(it.box.lo[0], it.box.lo[1], it.box.lo[2], it.box.hi[0]);
-        dn[b + 1] = mk4(it.box.hi[1], it.box.hi[2], lb.hi[0], lb.hi[1]);
-        dn[b + 2] = mk4(lb.hi[2], rb.lo[0], rb.lo[1], rb.lo[2]);
-        dn[b + 3] = mk4(u2f(lref), u2f(rref), u2f(lmeta), u2f(rmeta));
+        if (!std::isfinite(nd.lmax) || !std::isfinite(nd.rmin)) planes_finite = 0;
+        // interval stepping (desc_step) is exact iff both planes lie inside the node's own extent on the split axis
+        const bool nested = it.box.lo[ax] <= nd.lmax && nd.lmax <= it.box.hi[ax] && it.box.lo[ax] <= nd.rmin && nd.rmin <= it.box.hi[ax];
+        if (!nested) { lref |= kSlow; ++n_slow; }
+        lref |= ax << kAxisShift;
+        const size_t b = (size_t)branch_id[it.node];
+        dn[b] = mk4(nd.lmax, nd.rmin, u2f(lref), u2f(rref));
+        db[2 * b] = mk4(it.box.lo[0], it.box.lo[1], it.box.lo[2], it.box.hi[0]);
+        db[2 * b + 1] = mk4(it.box.hi[1], it.box.hi[2], 0.0f, 0.0f);
         todo.push_back({r, rb, it.depth + 1});
         todo.push_back({l, lb, it.depth + 1});
     }
     if (height > SQT_MAX_HEIGHT) return layout_fail(err, SQT_E_UNSUPPORTED, "BIH height %u exceeds SQT_MAX_HEIGHT=%d", height, SQT_MAX_HEIGHT);
-    for (uint32_t t = 0; t < s->n_tris; ++t)
-        if (s->tris[t].material >= s->n_mats) return layout_fail(err, SQT_E_INVALID, "triangle %u: material %u out of range", t, s->tris[t].material);
+    if (check_materials)
+        for (uint32_t t = 0; t < s->n_tris; ++t)
+            if (s->tris[t].material >= s->n_mats) return layout_fail(err, SQT_E_INVALID, "triangle %u: material %u out of range", t, s->tris[t].material);
 
     // materials: (reflective, surf) (emissive, emit) (emissive *^ emit, flags)
     std::vector<float4> dm((size_t)3 * s->n_mats);
@@ -148,8 +140,8 @@ inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, st
         if (s->nodes[0].a != 0 || (s->nodes[0].b & ~SQT_NODE_LEAF) != s->n_tris)
             return layout_fail(err, SQT_E_INVALID, "root leaf must cover tris[0..n_tris)");
     }
-    out.nodes.swap(dn); out.mats.swap(dm); out.leaves.swap(dl);
-    out.n_branches = n_br; out.height = height; out.terminate_on_black_ok = tob;
+    out.nodes.swap(dn); out.boxes.swap(db); out.mats.swap(dm);
+    out.n_branches = n_br; out.n_slow = n_slow; out.height = height; out.terminate_on_black_ok = tob; out.planes_finite = planes_finite;
     return SQT_OK;
 }
 

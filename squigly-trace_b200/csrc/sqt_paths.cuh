@@ -6,7 +6,7 @@
 //                        then put the lane's next ray into L.r and start it -- or set ST_EXIT when the lane
 //                        has no more work.
 //
-// The kernels in sqt_backend.cu run one warp-synchronous loop around these: regen for lanes that are done,
+// The kernels in sqt_kernels.cuh run one warp-synchronous loop around these: regen for lanes that are done,
 // traversal steps for lanes that are descending/returning, triangle steps for lanes inside a leaf
 // (sqt_core.cuh).  Lanes are independent, so any schedule yields the same per-lane results; tests/emu runs
 // each lane to completion on the host with the same functions.
@@ -416,17 +416,18 @@ struct CastPolicy {
 // One lane, run to completion on its own (tests/emu; lanes are independent so this equals any warp schedule).
 template <bool COUNT, class Policy>
 SQT_HD_NOINLINE void run_lane(const SceneView &sc, Policy &pol, Counters *cn) {
-    uint32_t stack[kStackWords];
+    float4 stack[kStackEntries];
     TravLane L;
     L.stack = stack;
     L.state = ST_DONE; L.sp = 0; L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
     L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
+    const LaneRay ra(L);
     for (;;) {
         if (L.state == ST_DONE) pol.template regen<COUNT>(sc, L, cn);
         if (L.state == ST_EXIT) break;
-        if (L.state == ST_RET) ret_step(sc, L);
-        if (L.state == ST_DESC) desc_step<COUNT>(sc, L, cn);
-        if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, cn);
+        if (L.state == ST_RET) ret_step(sc, L, ra);
+        if (L.state == ST_DESC) desc_step<COUNT>(sc, L, ra, cn);
+        if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, ra, cn);
         if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, cn);
     }
 }

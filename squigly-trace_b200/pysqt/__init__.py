@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "sqt_abi_version", "sqt_create", "sqt_destroy", "sqt_last_error", "sqt_upload_scene", "sqt_intersect_batch",
     "sqt_render", "sqt_render_resident", "sqt_download_image", "sqt_tone_map", "sqt_comm_unique_id", "sqt_comm_init",
     "sqt_comm_init_all", "sqt_render_group", "sqt_measure_fp32_peak", "sqt_measure_l2_bandwidth", "sqt_device_info", "sqt_set_option", "sqt_upload_spheres",
+    "sqt_upload_scene_group", "sqt_last_upload",
 ]
 
 
@@ -116,6 +117,8 @@ def b200():
         L.sqt_measure_l2_bandwidth.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.sqt_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.sqt_upload_spheres.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.sqt_upload_scene_group.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sqt_last_upload.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.sqt_device_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p]
         for name in ABI_SYMBOLS:
             if name not in ("sqt_last_error",):
@@ -269,6 +272,11 @@ class Context:
         self._keep = scene
         self._ck(self.L.sqt_upload_scene(self.h, C.byref(d)), "sqt_upload_scene")
 
+    def last_upload(self):
+        b, w, h = C.c_uint64(), C.c_double(), C.c_double()
+        self._ck(self.L.sqt_last_upload(self.h, C.byref(b), C.byref(w), C.byref(h)), "sqt_last_upload")
+        return dict(h2d_bytes=b.value, wall_ms=w.value, host_layout_ms=h.value)
+
     def upload_desc_raw(self, desc):
         return self.L.sqt_upload_scene(self.h, C.byref(desc))
 
@@ -337,6 +345,40 @@ class Context:
         v = C.c_double()
         self._ck(self.L.sqt_measure_l2_bandwidth(self.h, C.byref(v)), "sqt_measure_l2_bandwidth")
         return v.value
+
+
+class Group:
+    """Single-process group: one context per device, ncclCommInitAll underneath (what the Haskell host uses)."""
+
+    def __init__(self, devices):
+        self.ctxs = [Context(d) for d in devices]
+        self.arr = (C.c_void_p * len(self.ctxs))(*[c.h for c in self.ctxs])
+        L = b200()
+        rc = L.sqt_comm_init_all(self.arr, len(self.ctxs))
+        if rc:
+            raise SqtError("sqt_comm_init_all failed (%d): %s" % (rc, self.ctxs[0].last_error()))
+        self.L = L
+
+    def upload(self, scene):
+        d = scene.desc() if hasattr(scene, "desc") else scene
+        self._keep = scene
+        rc = self.L.sqt_upload_scene_group(self.arr, len(self.ctxs), C.byref(d))
+        if rc:
+            raise SqtError("sqt_upload_scene_group failed (%d): %s" % (rc, self.ctxs[0].last_error()))
+
+    def render(self, cam12, params, want_accum=True):
+        cam = camera_struct(cam12)
+        rgb8 = np.zeros((params.rows, params.cols, 3), np.uint8)
+        accum = np.zeros((params.rows, params.cols, 3), np.float32) if want_accum else None
+        st = Stats()
+        rc = self.L.sqt_render_group(self.arr, len(self.ctxs), C.byref(cam), C.byref(params), _p(rgb8), _p(accum), C.byref(st))
+        if rc:
+            raise SqtError("sqt_render_group failed (%d): %s" % (rc, self.ctxs[0].last_error()))
+        return dict(rgb8=rgb8, accum=accum, stats=st.as_dict())
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
 
 
 def comm_unique_id():

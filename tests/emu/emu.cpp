@@ -15,7 +15,7 @@ using namespace sqt;
 
 struct emu_scene {
     DeviceLayout lay;
-    std::vector<float4> tris, spheres;
+    std::vector<float4> tris, spheres, leaves;
     SceneView view;
     std::string err;
 };
@@ -40,8 +40,13 @@ emu_scene *emu_upload(const sqt_scene_desc *d) {
     s->tris.resize((size_t)3 * (d->n_tris ? d->n_tris : 1));
     if (d->n_tris) std::memcpy(s->tris.data(), d->tris, (size_t)d->n_tris * 48);
     SceneView v = {};
-    v.nodes = s->lay.nodes.data(); v.tris = s->tris.data(); v.mats = s->lay.mats.data(); v.leaves = s->lay.leaves.data();
-    v.leaf_cull = 1;
+    s->leaves.resize(2 * s->lay.leaf_first.size());
+    for (size_t k = 0; k < s->lay.leaf_first.size(); ++k) {
+        make_leaf_record(s->tris.data(), s->lay.leaf_first[k], s->lay.leaf_count[k], s->leaves[2 * k], s->leaves[2 * k + 1]);
+        if (s->lay.leaf_count[k] >= kLeafLong) s->tris[3 * (size_t)s->lay.leaf_first[k] + 2].w = u2f(s->lay.leaf_count[k]);
+    }
+    v.nodes = s->lay.nodes.data(); v.boxes = s->lay.boxes.data(); v.tris = s->tris.data(); v.mats = s->lay.mats.data(); v.leaves = s->leaves.data();
+    v.leaf_cull = 1; v.planes_finite = (uint32_t)s->lay.planes_finite;
     for (int k = 0; k < 3; ++k) { v.root_lo[k] = d->root_bounds[k]; v.root_hi[k] = d->root_bounds[3 + k]; }
     v.n_branches = s->lay.n_branches; v.n_tris = d->n_tris; v.n_mats = d->n_mats;
     v.root_is_leaf = (d->nodes[0].b & SQT_NODE_LEAF) ? 1u : 0u;
@@ -71,26 +76,31 @@ void emu_intersect_batch(emu_scene *s, const float *org, const float *dir, long 
     if (counters4) { counters4[0] = cn.branch_visits; counters4[1] = cn.child_box_tests; counters4[2] = cn.tri_tests; counters4[3] = cn.rays; counters4[4] = cn.leaves_culled; }
 }
 
-// The pool kernel's stack layout on the host: groups of 64 rays share ONE region in which their stacks are interleaved in
-// 32-byte granules (stack_word<512>), stride = 3 * height words rounded to 8 as launch_pool computes it.  The 64 rays are
-// stepped round-robin, one unit step each, so that an addressing error (overlap between slots, a stride too small) would
-// corrupt a neighbour's stack while it is live.  Canary words behind the region catch overruns.  Returns 0, or 1 if a
+// The pool kernel's stack layout on the host: groups of 64 rays share ONE region in which their stacks are interleaved
+// entry by entry (entry e of ray k at region[e * 64 + k], 16 bytes each; `height` entries per ray as launch_pool sizes it),
+// and their rays live in a structure-of-arrays pool read through PoolRay, exactly as k_paths_pool does.  The 64 rays are
+// stepped round-robin, one unit step each, so that an addressing error (overlap between slots, a region too small) would
+// corrupt a neighbour's stack while it is live.  Canary entries behind the region catch overruns.  Returns 0, or 1 if a
 // canary was overwritten.
 int emu_intersect_batch_interleaved(emu_scene *s, const float *org, const float *dir, long long n, int *tri_out, float *dist_out) {
     constexpr int P = 64;
-    int stride = (int)((3u * s->lay.height + 7u) & ~7u);
-    if (stride > kStackWords) stride = kStackWords;
-    if (stride < 8) stride = 8;
-    std::vector<uint32_t> region((size_t)P * stride + 64, 0xdeadbeefu);
+    const int depth = (int)std::max(1u, std::min<uint32_t>(s->lay.height, kStackEntries));
+    const float4 canary = float4{-7.0f, -7.0f, -7.0f, -7.0f};
+    std::vector<float4> region((size_t)P * depth + 64, canary);
+    std::vector<uint32_t> pool((size_t)9 * P, 0u);
     Counters cn = {};
     int bad = 0;
     for (long long base = 0; base < n; base += P) {
         const int m = (int)std::min<long long>(P, n - base);
         TravLane L[P];
         for (int k = 0; k < m; ++k) {
-            L[k].stack = region.data() + 8 * k;
+            L[k].stack = region.data() + k;
             L[k].r = Ray{org[3 * (base + k)], org[3 * (base + k) + 1], org[3 * (base + k) + 2], dir[3 * (base + k)], dir[3 * (base + k) + 1], dir[3 * (base + k) + 2]};
             start_ray<false>(s->view, L[k], &cn);
+            const float f[9] = {L[k].r.ox, L[k].r.oy, L[k].r.oz, L[k].r.dx, L[k].r.dy, L[k].r.dz, L[k].dfx, L[k].dfy, L[k].dfz};
+            for (int w = 0; w < 9; ++w) pool[(size_t)w * P + k] = f2u(f[w]);
+            // the steps below must read the ray from the pool only
+            L[k].r = Ray{-1.0f, -1.0f, -1.0f, -1.0f, -1.0f, -1.0f}; L[k].dfx = L[k].dfy = L[k].dfz = -1.0f;
         }
         for (bool any = true; any;) {
             any = false;
@@ -98,10 +108,14 @@ int emu_intersect_batch_interleaved(emu_scene *s, const float *org, const float 
                 TravLane &l = L[k];
                 if (l.state == ST_DONE) continue;
                 any = true;
-                if (l.state == ST_RET) ret_step<8 * P>(s->view, l);
-                else if (l.state == ST_DESC) desc_step<false, 8 * P>(s->view, l, &cn);
-                else if (l.state == ST_ENTER) enter_step<false>(s->view, l, &cn);
-                else if (l.state == ST_LEAF) tri_step<false>(s->view, l, &cn);
+                const PoolRay ra(pool.data() + k, P);
+                if (l.state == ST_RET) ret_step<P>(s->view, l, ra);
+                else if (l.state == ST_DESC) desc_step<false, P>(s->view, l, ra, &cn);
+                else if (l.state == ST_ENTER) enter_step<false>(s->view, l, ra, &cn);
+                else if (l.state == ST_LEAF) {
+                    const TriData d = tri_load(s->view, l.child + (uint32_t)l.i);
+                    tri_apply<false>(l, ra.ray(), d, &cn);
+                }
             }
         }
         for (int k = 0; k < m; ++k) {                        // report like BatchPolicy: position in the parsed list, -1 = Nothing
@@ -109,7 +123,7 @@ int emu_intersect_batch_interleaved(emu_scene *s, const float *org, const float 
             tri_out[base + k] = t < 0 ? -1 : ((uint32_t)t >= s->view.n_tris ? t : (int)f2u(s->tris[3 * (size_t)t + 2].z));
             dist_out[base + k] = t < 0 ? 0.0f : L[k].cur.dist;
         }
-        for (size_t c = (size_t)P * stride; c < region.size(); ++c) if (region[c] != 0xdeadbeefu) bad = 1;
+        for (size_t c = (size_t)P * depth; c < region.size(); ++c) if (std::memcmp(&region[c], &canary, 16) != 0) bad = 1;
     }
     return bad;
 }
@@ -211,20 +225,21 @@ long long emu_trace_lane(emu_scene *s, const sqt_camera *cam, const sqt_render_p
     SeqFetch fetch{0, rd.n_slots << rd.log2_s};
     uint16_t pm[SQT_MAX_DEPTH];
     PathPolicy<SeqFetch> pol(d, rd, fetch, st, pm);
-    uint32_t stack[kStackWords];
+    float4 stack[kStackEntries];
     TravLane L;
     L.stack = stack; L.state = ST_DONE; L.sp = 0; L.cur.tri = -1;
+    const LaneRay ra(L);
     long long n = 0;
     for (;;) {
         if (L.state == ST_DONE) { pol.regen<false>(s->view, L, &cn); if (n < cap) out[n] = 'R';
             n++; }
         if (L.state == ST_EXIT) break;
         if (L.state == ST_RET || L.state == ST_DESC) {
-            if (L.state == ST_RET) ret_step(s->view, L);
-            if (L.state == ST_DESC) desc_step<false>(s->view, L, &cn);
+            if (L.state == ST_RET) ret_step(s->view, L, ra);
+            if (L.state == ST_DESC) desc_step<false>(s->view, L, ra, &cn);
             if (n < cap) out[n] = 'T';
             n++;
-        } else if (L.state == ST_ENTER) { enter_step<false>(s->view, L, &cn); if (n < cap) out[n] = 'E'; n++; }
+        } else if (L.state == ST_ENTER) { enter_step<false>(s->view, L, ra, &cn); if (n < cap) out[n] = 'E'; n++; }
         else if (L.state == ST_LEAF) { tri_step<false>(s->view, L, &cn); if (n < cap) out[n] = 'L'; n++; }
     }
     return n < cap ? n : cap;
@@ -238,15 +253,16 @@ void emu_leaf_cull_stats(emu_scene *s, const float *org, const float *dir, long 
     const uint32_t saved_cull = s->view.leaf_cull;
     s->view.leaf_cull = 0;
     Counters cn = {};
-    uint32_t stack[kStackWords];
+    float4 stack[kStackEntries];
     for (long long i = 0; i < n; ++i) {
         TravLane L; L.stack = stack;
+        const LaneRay ra(L);
         L.r = Ray{org[3 * i], org[3 * i + 1], org[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
         start_ray<false>(s->view, L, &cn);
         while (L.state != ST_DONE) {
-            if (L.state == ST_RET) ret_step(s->view, L);
-            if (L.state == ST_DESC) desc_step<false>(s->view, L, &cn);
-            if (L.state == ST_ENTER) enter_step<false>(s->view, L, &cn);
+            if (L.state == ST_RET) ret_step(s->view, L, ra);
+            if (L.state == ST_DESC) desc_step<false>(s->view, L, ra, &cn);
+            if (L.state == ST_ENTER) enter_step<false>(s->view, L, ra, &cn);
             if (L.state == ST_LEAF) {
                 const uint32_t first = L.child, count = (uint32_t)L.i + 1;
                 float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
