@@ -405,7 +405,7 @@ static int persistent_grid(sqt_ctx *ctx, K kernel, long long nwork) {
 struct PoolPlan { int grid = 0; size_t smem = 0; int depth = 1, pm_stride = 8; };
 template <bool COUNT, int K>
 static int pool_step(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems, bool launch) {
-    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 3 * (32 * K / 4)) * sizeof(uint32_t);
+    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 3 * (32 * K / 4) + 64) * sizeof(uint32_t);
     auto kern = k_paths_pool<COUNT, K>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -655,6 +655,18 @@ static void fill_stats(sqt_ctx *ctx, sqt_stats *s, uint32_t launches) {
     s->mt_pass_a = ctx->h_stats->mt_pass_a; s->mt_pass_u = ctx->h_stats->mt_pass_u;
     s->mt_pass_v = ctx->h_stats->mt_pass_v; s->mt_accept = ctx->h_stats->mt_accept;
     s->kernel_launches = launches;
+    if (getenv("SQT_DEBUG_STATS") && ctx->h_stats->dbg[0]) {        // scheduler diagnostics of the instrumented pool kernel (development)
+        const unsigned long long *d = ctx->h_stats->dbg;
+        const double rays = (double)ctx->h_stats->rays;
+        fprintf(stderr, "[sqt pool] per ray: T rounds %.3f (fill %.1f)  L rounds %.3f (fill %.1f)  R rounds %.3f (fill %.1f)\n", d[0] / rays, (double)d[3] / d[0],
+                d[1] / rays, (double)d[4] / (d[1] ? d[1] : 1), d[2] / rays, (double)d[5] / (d[2] ? d[2] : 1));
+        fprintf(stderr, "[sqt pool] T burst, lanes per step  ret:");
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %.1f", (double)d[16 + k] / d[0]);
+        fprintf(stderr, "  desc:");
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %.1f", (double)d[8 + k] / d[0]);
+        fprintf(stderr, "\n[sqt pool] L passes %.3f per L round, rays with triangles %.1f, tests %.1f, chunks %.2f per pass\n", (double)d[24] / (d[1] ? d[1] : 1),
+                (double)d[25] / (d[24] ? d[24] : 1), (double)d[26] / (d[24] ? d[24] : 1), (double)d[27] / (d[24] ? d[24] : 1));
+    }
 }
 
 extern "C" int sqt_render_resident(sqt_ctx *ctx, const sqt_camera *cam, const sqt_render_params *p, sqt_stats *stats) {

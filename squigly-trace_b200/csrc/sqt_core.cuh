@@ -208,6 +208,28 @@ SQT_HD bool moller_trumbore(const float4 &a0, const float4 &a1, const float4 &a2
     return true;
 }
 
+// The first two guards of mollerTrumbore only (same operations, same order): true iff the test gets past `a` and `u`.
+// The pool kernel runs this for every (ray, triangle) pair and the full test only for the ~18 % that survive.
+SQT_HD bool moller_trumbore_au(const float4 &a0, const float4 &a1, const float4 &a2, const Ray &r, int &stage) {
+    const float eps = 0.0001f;
+    const float v0x = a0.x, v0y = a0.y, v0z = a0.z;
+    const float e1x = a0.w, e1y = a1.x, e1z = a1.y;
+    const float e2x = a1.z, e2y = a1.w, e2z = a2.x;
+    float hx = XSUB(XMUL(r.dy, e2z), XMUL(r.dz, e2y));
+    float hy = XSUB(XMUL(r.dz, e2x), XMUL(r.dx, e2z));
+    float hz = XSUB(XMUL(r.dx, e2y), XMUL(r.dy, e2x));
+    float a = dot3(e1x, e1y, e1z, hx, hy, hz);
+    stage = 0;
+    if (a > -eps && a < eps) return false;
+    stage = 1;
+    float f = XRCP(a);
+    float sx = XSUB(r.ox, v0x), sy = XSUB(r.oy, v0y), sz = XSUB(r.oz, v0z);
+    float u = XMUL(f, dot3(sx, sy, sz, hx, hy, hz));
+    if (u < 0.0f || u > 1.0f) return false;
+    stage = 2;
+    return true;
+}
+
 // ------------------------------------------------------------------------------ leaf records
 // Leaf record (see "device records") of the leaf tris[first .. first + cnt): the tight box of the triangles as
 // Moller-Trumbore sees them (v0, v0 + e1, v0 + e2), rounded outwards, and their longest edge, rounded up.  Used only by

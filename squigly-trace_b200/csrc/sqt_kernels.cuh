@@ -26,6 +26,7 @@ struct DeviceStats {
     unsigned long long mt_pass_a, mt_pass_u, mt_pass_v, mt_accept;
     unsigned long long n_hit;           // length of the pixel list k_primary builds
     unsigned long long work_next[256];  // dynamic work counters of the path kernels, one per round
+    unsigned long long dbg[48];         // scheduler diagnostics of k_paths_pool (instrumented variant only), see SQT_DEBUG_STATS
 };
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(128, SQT_WL_MIN_BLOCKS) k_paths(SceneView sc, 
 // step kind at any time (tests/sched_sim.py); regrouping rays lifts that limit.  Scheduling never changes a result: every
 // ray runs the same unit steps of sqt_core.cuh in the same order (test_every_path_kernel_scheduler_is_bit_exact).
 #ifndef SQT_POOL_MIN_BLOCKS
-#define SQT_POOL_MIN_BLOCKS 9
+#define SQT_POOL_MIN_BLOCKS 8
 #endif
 // burst_t: traversal steps per T round (at most); t_leave: end the burst early once at most this many lanes still traverse;
 // c_min: serve the regeneration queue only when it holds at least this many rays (or nothing else can run)
@@ -285,11 +286,12 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                                                     float4 *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath, int stack_depth, int pm_stride) {
     extern __shared__ uint32_t pool_smem[];
     constexpr int P = 32 * K;
-    constexpr int WARP_WORDS = P * PF_WORDS + 3 * (P / 4);
+    constexpr int WARP_WORDS = P * PF_WORDS + 3 * (P / 4) + 64;
     const unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t *pool = pool_smem + warp * WARP_WORDS;
     uint8_t *queue = (uint8_t *)(pool + P * PF_WORDS);                          // queue[k * P + i], k = KT, KL, KR
+    uint32_t *survivors = pool + P * PF_WORDS + 3 * (P / 4);                    // ring of 64 (triangle | gathering lane << 27)
     const int gslot0 = (int)((blockIdx.x * (blockDim.x >> 5) + warp) * P);     // < 2^31: at most a few hundred thousand pool slots exist
     float4 *wstack = gstack + (size_t)gslot0 * (size_t)stack_depth;            // entry e of slot s at wstack[e * P + s]
 #define PW(f, slot) pool[(f) * P + (slot)]
@@ -309,6 +311,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
     __syncwarp(FULL);
     const unsigned lt_mask = (1u << lane) - 1u;
     int q_head[3] = {0, 0, 0}, q_cnt[3] = {0, 0, P};                       // warp-uniform
+    unsigned long long dbg_rounds[3] = {0, 0, 0}, dbg_sel[3] = {0, 0, 0}, dbg_desc[8] = {}, dbg_ret[8] = {}, dbg_leaf[4] = {};
     for (;;) {
         // ---- pick the longest queue (regeneration only in batches, or when nothing else can run)
         const int c_r = (q_cnt[KR] >= tn.c_min || (q_cnt[KT] | q_cnt[KL]) == 0) ? q_cnt[KR] : 0;
@@ -335,6 +338,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         L.stack = nullptr;
         L.state = ST_EXIT;
         const PoolRay ra(pool + slot, P);
+        if (COUNT) { dbg_rounds[kind] += 1; dbg_sel[kind] += n_sel; }
         if (kind == KT) {
             // ---- traversal steps: stack pops + branch visits
             uint32_t fl = 0u;
@@ -346,7 +350,9 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
             }
             for (int b = 0; b < tn.burst_t; ++b) {
+                if (COUNT) { dbg_ret[b < 7 ? b : 7] += __popc(__ballot_sync(FULL, L.state == ST_RET)); }
                 if (L.state == ST_RET) ret_step<P>(sc, L, ra);
+                if (COUNT) { dbg_desc[b < 7 ? b : 7] += __popc(__ballot_sync(FULL, L.state == ST_DESC)); }
                 if (L.state == ST_DESC) desc_step<COUNT, P>(sc, L, ra, &cn);
                 if (__popc(__ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET)) <= tn.t_leave) break;
             }
@@ -375,7 +381,37 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             }
             __syncwarp(FULL);
             // Stage 2: all (ray, triangle) tests of the gathered rays, 32 per step.  Test p of a pass belongs to the lane
-            // whose inclusive scan first exceeds p; within a ray tests run from its last triangle to its first.
+            // whose inclusive scan first exceeds p; within a ray tests run from its last triangle to its first.  A test is
+            // first run to the `u` guard only (moller_trumbore_au); the ~18 % that survive are appended -- in test order --
+            // to a small ring in shared memory and re-run in full, 32 at a time, so that the expensive tail of
+            // Moller-Trumbore (second cross product, v / t guards, point, IEEE sqrt) also executes with all lanes.
+            int n_surv = 0, surv_head = 0;                                  // warp-uniform
+            auto run_survivors = [&](int n) {
+                const uint32_t e = lane < n ? survivors[(surv_head + lane) & 63] : 0u;
+                const int oslot = __shfl_sync(FULL, slot, (int)(e >> 27));
+                const uint32_t idx = e & kLeafFirstMask;
+                bool hit = false;
+                float t = 0.0f, dist = 0.0f;
+                if (lane < n) {
+                    const TriData d = tri_load(sc, idx);
+                    const Ray r = PoolRay(pool + oslot, P).ray();
+                    int stage;
+                    hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
+                    if (COUNT) { cn.mt_pass_v += stage >= 3; cn.mt_accept += stage >= 4; }
+                }
+                unsigned hm = __ballot_sync(FULL, hit);
+                while (hm != 0u) {                                          // fold each accepted hit into its ray, in test order
+                    const int src = __ffs(hm) - 1;
+                    hm &= hm - 1u;
+                    if (lane == src) {                                      // fold_earlier on the ray's best hit in the pool
+                        if ((int)PW(PF_CTRI, oslot) < 0 || !cmp_gt(dist, u2f(PW(PF_CDIST, oslot)))) {
+                            PW(PF_CTRI, oslot) = idx; PW(PF_CT, oslot) = f2u(t); PW(PF_CDIST, oslot) = f2u(dist);
+                        }
+                    }
+                    __syncwarp(FULL);
+                }
+                surv_head = (surv_head + n) & 63; n_surv -= n;
+            };
             for (;;) {
                 const int c = rem < 1024 ? rem : 1024;                     // a pathological leaf is worked off over several passes
                 int incl = c;
@@ -386,6 +422,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 }
                 const int total = __shfl_sync(FULL, incl, 31);
                 if (total == 0) break;
+                if (COUNT) { dbg_leaf[0] += 1; dbg_leaf[1] += __popc(__ballot_sync(FULL, c > 0)); dbg_leaf[2] += total; dbg_leaf[3] += (total + 31) / 32; }
                 const int tri_base = (int)first + rem - 1 + (incl - c);     // triangle of test p (of this lane's ray) = tri_base - p
                 for (int base = 0; base < total; base += 32) {
                     const int pr = base + lane;
@@ -397,30 +434,37 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                     }
                     const int oslot = __shfl_sync(FULL, slot, own);
                     const uint32_t idx = (uint32_t)(__shfl_sync(FULL, tri_base, own) - pr);
-                    bool hit = false;
-                    float t = 0.0f, dist = 0.0f;
+                    bool pass = false;
                     if (pr < total) {
                         const TriData d = tri_load(sc, idx);
                         const Ray r = PoolRay(pool + oslot, P).ray();
                         int stage;
-                        hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
-                        if (COUNT) { cn.mt_pass_a += stage >= 1; cn.mt_pass_u += stage >= 2; cn.mt_pass_v += stage >= 3; cn.mt_accept += stage >= 4; }
+                        pass = moller_trumbore_au(d.a0, d.a1, d.a2, r, stage);
+                        if (COUNT) { cn.mt_pass_a += stage >= 1; cn.mt_pass_u += stage >= 2; }
                     }
-                    unsigned hm = __ballot_sync(FULL, hit);
-                    while (hm != 0u) {                                      // rare: fold each accepted hit into its ray, in test order
-                        const int src = __ffs(hm) - 1;
-                        hm &= hm - 1u;
-                        if (lane == src) {                                  // fold_earlier on the ray's best hit in the pool
-                            if ((int)PW(PF_CTRI, oslot) < 0 || !cmp_gt(dist, u2f(PW(PF_CDIST, oslot)))) {
-                                PW(PF_CTRI, oslot) = idx; PW(PF_CT, oslot) = f2u(t); PW(PF_CDIST, oslot) = f2u(dist);
-                            }
-                        }
-                        __syncwarp(FULL);
-                    }
+                    const unsigned pm = __ballot_sync(FULL, pass);
+                    if (pass) survivors[(surv_head + n_surv + __popc(pm & lt_mask)) & 63] = idx | ((uint32_t)own << 27);
+                    n_surv += __popc(pm);
+                    __syncwarp(FULL);
+                    if (n_surv >= 32) run_survivors(32);
                 }
                 rem -= c;
             }
-            if (act) { L.state = ST_RET; PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)ST_RET; }
+            if (n_surv > 0) run_survivors(n_surv);
+            // Stage 3: every gathered ray now holds the result of its leaf (or Nothing, if the leaf was culled or empty):
+            // pop its stack right here, with all gathered lanes, instead of in a traversal round -- a third of the rays go
+            // straight on to another leaf (the far child) or are finished and never need a traversal round in between.
+            L.stack = wstack + slot;
+            if (act) {
+                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
+                L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
+                L.tmin = 0.0f; L.tmax = 0.0f; L.child = 0u;
+                L.state = ST_RET;
+                ret_step<P>(sc, L, ra);
+                PW(PF_CHILD, slot) = L.child; PW(PF_TMIN, slot) = f2u(L.tmin); PW(PF_TMAX, slot) = f2u(L.tmax);
+                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
+                PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
+            }
         } else {
             // ---- regeneration: consume the finished hit, shade, start the next ray (or the next sample); staged, all
             //      gathered lanes together (path_regen_warp)
@@ -472,6 +516,11 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         __syncwarp(FULL);
     }
 #undef PW
+    if (COUNT && lane == 0) {
+        for (int k = 0; k < 3; ++k) { atomicAdd(&ds->dbg[k], dbg_rounds[k]); atomicAdd(&ds->dbg[3 + k], dbg_sel[k]); }
+        for (int k = 0; k < 8; ++k) { atomicAdd(&ds->dbg[8 + k], dbg_desc[k]); atomicAdd(&ds->dbg[16 + k], dbg_ret[k]); }
+        for (int k = 0; k < 4; ++k) atomicAdd(&ds->dbg[24 + k], dbg_leaf[k]);
+    }
     flush_stats(ds, st, cn, COUNT);
 }
 

@@ -7,7 +7,7 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(raw.splitlines()))
 # function line ranges from the sources (top-level SQT_HD / __device__ / __global__ definitions)
 ranges = {}
-for f in ("sqt_core.cuh", "sqt_paths.cuh", "sqt_backend.cu"):
+for f in ("sqt_core.cuh", "sqt_paths.cuh", "sqt_kernels.cuh", "sqt_backend.cu"):
     src = open(os.path.join(ROOT, "squigly-trace_b200", "csrc", f)).read().splitlines()
     starts = []
     for i, l in enumerate(src, 1):

@@ -13,7 +13,7 @@ hs = pysqt.HostScene.load(os.path.join(data, "scene.obj"), data)
 cam = pysqt.load_camera(os.path.join(data, "camera"))
 ctx = pysqt.Context(0)
 ctx.upload(hs)
-p = pysqt.make_params(W, H, SPP, max_depth=DEPTH, seed=0)
+p = pysqt.make_params(W, H, SPP, max_depth=DEPTH, seed=0, flags=int(os.environ.get("SQT_PROF_FLAGS", "0")))     # 1 = instrumented kernels
 for i in range(2):
     st = ctx.render_resident(cam, p)
     print("render %dx%d %dspp depth%d: device %.2f ms paths %.2f ms primary %.3f ms rays %d -> %.1f Mrays/s" % (
