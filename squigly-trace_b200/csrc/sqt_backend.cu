@@ -58,7 +58,7 @@ struct sqt_ctx {
     uint8_t *h_rgb8 = nullptr; float *h_accum = nullptr; long long cap_host_pixels = 0;
     Tune tune = {12, 0, 12};
     int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
-    PoolTune pool_tune = {4, 6, 16};
+    PoolTune pool_tune = {4, 10, 16};
     int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1
     float4 *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0, cap_stack_entries = 0;
     bool comm_broken = false;           // the communicator was aborted after a rank failed
@@ -405,7 +405,7 @@ static int persistent_grid(sqt_ctx *ctx, K kernel, long long nwork) {
 struct PoolPlan { int grid = 0; size_t smem = 0; int depth = 1, pm_stride = 8; };
 template <bool COUNT, int K>
 static int pool_step(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems, bool launch) {
-    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 3 * (32 * K / 4) + 64) * sizeof(uint32_t);
+    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 3 * (32 * K / 4) + 64 + 96) * sizeof(uint32_t);
     auto kern = k_paths_pool<COUNT, K>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

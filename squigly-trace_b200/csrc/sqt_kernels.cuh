@@ -286,12 +286,14 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                                                     float4 *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath, int stack_depth, int pm_stride) {
     extern __shared__ uint32_t pool_smem[];
     constexpr int P = 32 * K;
-    constexpr int WARP_WORDS = P * PF_WORDS + 3 * (P / 4) + 64;
+    constexpr int WARP_WORDS = P * PF_WORDS + 3 * (P / 4) + 64 + 96;
     const unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t *pool = pool_smem + warp * WARP_WORDS;
     uint8_t *queue = (uint8_t *)(pool + P * PF_WORDS);                          // queue[k * P + i], k = KT, KL, KR
     uint32_t *survivors = pool + P * PF_WORDS + 3 * (P / 4);                    // ring of 64 (triangle | gathering lane << 27)
+    uint32_t *lane_slot = survivors + 64;                                       // leaf round: the pool slot each lane gathered
+    uint32_t *own_tab = lane_slot + 32;                                         // leaf round: per owner rank (lane, triangle base)
     const int gslot0 = (int)((blockIdx.x * (blockDim.x >> 5) + warp) * P);     // < 2^31: at most a few hundred thousand pool slots exist
     float4 *wstack = gstack + (size_t)gslot0 * (size_t)stack_depth;            // entry e of slot s at wstack[e * P + s]
 #define PW(f, slot) pool[(f) * P + (slot)]
@@ -366,6 +368,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             uint32_t fl = 0u;
             uint32_t first = 0u;
             int rem = 0;                                                    // triangles of this lane's ray still to test
+            lane_slot[lane] = (uint32_t)slot;
             if (act) {
                 fl = PW(PF_FLAGS, slot);
                 L.child = PW(PF_CHILD, slot);
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             int n_surv = 0, surv_head = 0;                                  // warp-uniform
             auto run_survivors = [&](int n) {
                 const uint32_t e = lane < n ? survivors[(surv_head + lane) & 63] : 0u;
-                const int oslot = __shfl_sync(FULL, slot, (int)(e >> 27));
+                const int oslot = (int)lane_slot[e >> 27];
                 const uint32_t idx = e & kLeafFirstMask;
                 bool hit = false;
                 float t = 0.0f, dist = 0.0f;
@@ -423,17 +426,29 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 const int total = __shfl_sync(FULL, incl, 31);
                 if (total == 0) break;
                 if (COUNT) { dbg_leaf[0] += 1; dbg_leaf[1] += __popc(__ballot_sync(FULL, c > 0)); dbg_leaf[2] += total; dbg_leaf[3] += (total + 31) / 32; }
-                const int tri_base = (int)first + rem - 1 + (incl - c);     // triangle of test p (of this lane's ray) = tri_base - p
+                // The rays that still have triangles ("owners"), in lane order, own consecutive ranges of tests.  Each owner
+                // publishes (its lane, triangle of its test 0 + that test's position) in a small table by rank; per chunk of 32
+                // tests the owners whose range starts inside the chunk set one bit each (one REDUX), and a test finds its
+                // owner's rank by counting the bits at or below its position -- no search, two table reads.
+                const unsigned om = __ballot_sync(FULL, c > 0);
+                if (c > 0) {
+                    const int rank = __popc(om & lt_mask);
+                    own_tab[rank] = (uint32_t)lane;
+                    own_tab[32 + rank] = (uint32_t)((int)first + rem - 1 + (incl - c));      // triangle of test p of this ray = that - p
+                }
+                __syncwarp(FULL);
+                const int start = incl - c;
+                int started = 0;                                            // owners whose range starts before `base` (warp-uniform)
                 for (int base = 0; base < total; base += 32) {
                     const int pr = base + lane;
-                    int own = 0;
-#pragma unroll
-                    for (int s = 16; s > 0; s >>= 1) {
-                        const int v = __shfl_sync(FULL, incl, own + s - 1);
-                        if (v <= pr) own += s;
-                    }
-                    const int oslot = __shfl_sync(FULL, slot, own);
-                    const uint32_t idx = (uint32_t)(__shfl_sync(FULL, tri_base, own) - pr);
+                    const unsigned rel = (unsigned)(start - base);
+                    const unsigned sm = __reduce_or_sync(FULL, (c > 0 && rel < 32u) ? (1u << rel) : 0u);
+                    int k = started + __popc(sm & (0xffffffffu >> (31 - lane))) - 1;
+                    started += __popc(sm);
+                    if (pr >= total) k = 0;
+                    const int own = (int)own_tab[k];
+                    const uint32_t idx = own_tab[32 + k] - (uint32_t)pr;
+                    const int oslot = (int)lane_slot[own];
                     bool pass = false;
                     if (pr < total) {
                         const TriData d = tri_load(sc, idx);

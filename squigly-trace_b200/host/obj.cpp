@@ -48,9 +48,19 @@ class Reader {
         if (p < s_.size() && s_[p] == '.') ++p;
         while (p < s_.size() && std::isdigit((unsigned char)s_[p])) ++p;
         std::string tok = s_.substr(b, p - b);
-        bool has_digit = false;
-        for (char c : tok) has_digit |= std::isdigit((unsigned char)c) != 0;
-        if (!has_digit) return false;        // Haskell `read` would throw "Prelude.read: no parse"
+        // Haskell `read :: String -> Float` accepts -?digits and -?digits.digits only: "1.", ".5", "-.5", "-" and "" are
+        // "Prelude.read: no parse" (the reference crashes on them; here the parse fails)
+        {
+            size_t q = 0;
+            if (q < tok.size() && tok[q] == '-') ++q;
+            const size_t d1 = q;
+            while (q < tok.size() && std::isdigit((unsigned char)tok[q])) ++q;
+            if (q == d1) return false;
+            if (q < tok.size()) {                 // tok[q] == '.'
+                ++q;
+                if (q >= tok.size()) return false;
+            }
+        }
         out = std::strtof(tok.c_str(), nullptr);
         pos_ = p;
         return true;
@@ -111,7 +121,12 @@ std::pair<std::string, std::vector<Object>> loadObjFile(const std::string &text)
         if (!r.string("usemtl")) patternFail("(mtllib', objs)");      // materialName (Obj.hs:125-126)
         r.spaces();
         if (!r.word(o.mtl)) patternFail("(mtllib', objs)");
-        if (r.string("s on") || r.string("s off")) r.spaces();        // optional parseS (Obj.hs:134-135)
+        // optional parseS (Obj.hs:134-135): try (string "s on") <|> string "s off".  parsec's `string` consumes what it
+        // matched before it fails, so any other text starting with 's' is a parse error (the reference aborts), not a skip
+        if (r.peek() == 's') {
+            if (!(r.string("s on") || r.string("s off"))) patternFail("(mtllib', objs)");
+            r.spaces();
+        }
         while (r.peek() == 'f') {                     // face (Obj.hs:137-147)
             r.skip(); r.spaces();
             Face f;
@@ -120,6 +135,9 @@ std::pair<std::string, std::vector<Object>> loadObjFile(const std::string &text)
         }
         objs.push_back(std::move(o));
     }
+    // parsec's `parse` does not demand end of input and neither does the reference: whatever follows the last object is
+    // ignored.  Say so, a truncated scene is otherwise rendered silently.
+    if (!r.atEnd()) std::fprintf(stderr, "squigly: warning: .obj input ignored from offset %zu on (no further `o` object; Obj.hs:96-97 stops here too)\n", r.pos());
     return {lib, std::move(objs)};
 }
 

@@ -56,6 +56,7 @@ emu_scene *emu_upload(const sqt_scene_desc *d) {
 const char *emu_error(emu_scene *s) { return s->err.c_str(); }
 void emu_free(emu_scene *s) { delete s; }
 int emu_height(emu_scene *s) { return (int)s->lay.height; }
+int emu_slow_nodes(emu_scene *s) { return (int)s->lay.n_slow; }
 void emu_set_leaf_cull(emu_scene *s, int on) { s->view.leaf_cull = on ? 1u : 0u; }
 void emu_set_spheres(emu_scene *s, const sqt_sphere *sp, unsigned n) {
     s->spheres.assign((size_t)2 * (n ? n : 1), float4{0, 0, 0, 0});

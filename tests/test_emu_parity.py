@@ -148,3 +148,64 @@ def test_sphere_extension(host_scene, camera):
 def _plain(osc):
     osc.set_spheres([])
     return osc
+
+
+def _big_overlapping_triangles(n, seed):
+    """Large triangles whose extents overlap heavily: the +-0.001 planes of many nodes stick out of the clipped box they
+    split (lmax > hi[ax] or rmin < lo[ax]), which is the case the interval stepping of desc_step must hand to the literal
+    six-slab path (nodes flagged kSlow at upload)."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, (n, 1, 3))
+    e = rng.normal(size=(n, 3, 3)) * rng.uniform(0.05, 1.5, (n, 1, 1))
+    v9 = (c + e).reshape(n, 9).astype(np.float32)
+    # a few axis-aligned slivers that end exactly on the bounds of the whole set
+    lo, hi = v9.reshape(-1, 3).min(0), v9.reshape(-1, 3).max(0)
+    extra = np.array([[lo[0], lo[1], lo[2], hi[0], lo[1], lo[2], hi[0], hi[1], lo[2]],
+                      [lo[0], hi[1], hi[2], hi[0], hi[1], hi[2], lo[0], lo[1], hi[2]]], np.float32)
+    # long triangles with one vertex exactly ON a face of the bounds and their centroid far inside: wherever such a triangle
+    # falls on the low side of a split along that axis, lmax = 0.001 + its vertex exceeds the (unpadded) root extent
+    k = n // 8
+    far = rng.uniform(lo, hi, (k, 3, 3)).astype(np.float32) * np.float32(0.3)
+    face = rng.integers(0, 6, k)
+    for i in range(k):
+        ax = face[i] % 3
+        far[i, 0, ax] = hi[ax] if face[i] < 3 else lo[ax]
+    v9 = np.concatenate([v9, extra, far.reshape(k, 9)])
+    mats = np.array([[0.3, .5, .5, .5, 0, 0, 0, 0]], np.float32)
+    return v9, np.zeros(len(v9), np.int32), mats
+
+
+def test_nodes_whose_planes_leave_their_box_take_the_literal_path():
+    v9, mi, mats = _big_overlapping_triangles(3000, 17)
+    osc, hs = build_pair(v9, mi, mats)
+    e = Emu(hs)
+    import ctypes as C
+    from common import emu_lib
+    emu_lib().emu_slow_nodes.restype = C.c_int
+    emu_lib().emu_slow_nodes.argtypes = [C.c_void_p]
+    assert emu_lib().emu_slow_nodes(e.h) > 20, "the scene is meant to exercise the slow path"
+    org, dirs = random_rays(20000, 23, lo=-3, hi=3)
+    o2, d2 = adversarial_rays(v9, seed=3, n_each=64)
+    org = np.concatenate([org, o2]); dirs = np.concatenate([dirs, d2])
+    want = osc.intersect_batch(org, dirs, counters=True)
+    e.set_leaf_cull(False)
+    got = e.intersect_batch(org, dirs)
+    assert_same_hits(got, want, "slow nodes")
+    assert got[3]["branch_visits"] == int(want[3][0]) and got[3]["tri_tests"] == int(want[3][3])
+    e.set_leaf_cull(True)
+    assert_same_hits(e.intersect_batch(org, dirs), want, "slow nodes, culling on")
+    tri, dist, bad = e.intersect_batch_interleaved(org, dirs)
+    assert bad == 0 and np.array_equal(tri, want[0]) and np.array_equal(dist.view(np.uint32), want[1].view(np.uint32))
+
+
+def test_non_finite_planes_disable_interval_stepping():
+    """A vertex at infinity makes box planes infinite (and slab values NaN): every ray must then take the literal path with
+    the Haskell min/max (operand order matters with NaN), like the oracle."""
+    v9, mi, mats = scenes.cornell_box(600)
+    v9 = v9.copy()
+    v9[5, 0] = np.inf
+    v9[17, 4] = -np.inf
+    osc, hs = build_pair(v9, mi, mats)
+    e = Emu(hs)
+    org, dirs = random_rays(8000, 29, lo=-2.5, hi=2.5)
+    assert_same_hits(e.intersect_batch(org, dirs), osc.intersect_batch(org, dirs), "infinite planes")

@@ -432,3 +432,89 @@ def test_full_size_properties_1080p(gpu_ctx, host_scene, oracle_scene, camera):
         assert np.array_equal(bits(acc[r]), bits(row)), "row %d differs" % r
     again = gpu_ctx.render(camera, p)["accum"]
     assert np.array_equal(bits(acc), bits(again))
+
+
+# ------------------------------------------------------------------ interval stepping corner cases on the device
+def test_slow_nodes_and_infinite_planes_bit_exact(gpu_ctx):
+    """Nodes whose +-0.001 planes leave their clipped box (literal six-slab path inside desc_step) and a tree with infinite
+    planes (every ray on the literal path): same hits as the oracle, with the culling on and off."""
+    from test_emu_parity import _big_overlapping_triangles
+    v9, mi, mats = _big_overlapping_triangles(3000, 17)
+    osc, hs = build_pair(v9, mi, mats)
+    gpu_ctx.upload(hs)
+    org, dirs = random_rays(200_000, 23, lo=-3, hi=3)
+    o2, d2 = adversarial_rays(v9, seed=3, n_each=128)
+    org = np.concatenate([org, o2]); dirs = np.concatenate([dirs, d2])
+    want = osc.intersect_batch(org, dirs, counters=True)
+    assert_same_hits(gpu_ctx.intersect_batch(org, dirs), want, "slow nodes")
+    with no_leaf_cull(gpu_ctx):
+        got = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
+    assert_same_hits(got, want, "slow nodes, no culling")
+    assert got[3]["branch_visits"] == int(want[3][0]) and got[3]["tri_tests"] == int(want[3][3])
+    out = gpu_ctx.render(default_cam(), pysqt.make_params(96, 64, 6, max_depth=6, seed=2))
+    ref = osc.render(default_cam(), O.make_params(96, 64, 6, max_depth=6, seed=2, trig=1))
+    assert np.array_equal(bits(out["accum"]), bits(ref["accum"]))
+    v9, mi, mats = scenes.cornell_box(600)
+    v9 = v9.copy(); v9[5, 0] = np.inf; v9[17, 4] = -np.inf
+    osc, hs = build_pair(v9, mi, mats)
+    gpu_ctx.upload(hs)
+    org, dirs = random_rays(100_000, 29, lo=-2.5, hi=2.5)
+    assert_same_hits(gpu_ctx.intersect_batch(org, dirs), osc.intersect_batch(org, dirs), "infinite planes")
+
+
+def default_cam():
+    return pysqt.load_camera(pysqt.ROOT + "/data/camera")
+
+
+# ------------------------------------------------------------------ BASELINE.json configs 3, 4, 5 at their full size
+def _full_size_checks(ctx, hs, osc, cam, cfg, n_pixels, seed=0):
+    """Size-independent checks in the style of test_baseline_config2_at_full_size: exact sample accounting, pixels whose
+    primary ray misses are exactly black, `n_pixels` hit pixels re-rendered by the oracle with ALL their samples match bit
+    for bit (so every accumulation round adds in sample order), RGB8 = the oracle's tone map of the device's sums."""
+    W, H, spp, depth = cfg["width"], cfg["height"], cfg["spp"], cfg["depth"]
+    ctx.upload(hs)
+    out = ctx.render(cam, pysqt.make_params(W, H, spp, max_depth=depth, seed=seed))
+    acc, st = out["accum"], out["stats"]
+    assert st["samples"] == W * H * spp
+    org, dirs = O.make_rays(O.make_params(W, H, 1), cam)
+    tri = ctx.intersect_batch(org, dirs)[0]
+    miss = (tri < 0).reshape(H, W)
+    assert np.all(acc[miss] == 0)
+    op = O.make_params(W, H, spp, max_depth=depth, seed=seed, trig=1)
+    rng = np.random.default_rng(5)
+    hit_pixels = np.flatnonzero(~miss.ravel())
+    assert len(hit_pixels) > 1000
+    for pix in rng.choice(hit_pixels, n_pixels, replace=False):
+        want = O.render_window(osc, cam, op, int(pix), int(pix) + 1)
+        assert np.array_equal(bits(acc.reshape(-1, 3)[pix]), bits(want[0])), "pixel %d" % pix
+    assert np.array_equal(out["rgb8"], O.tone_map(acc, spp, trig=1))
+    return st
+
+
+def test_baseline_config3_at_full_size(gpu_ctx, camera):
+    """BASELINE.json configs[2]: synthetic Cornell box (~10 k triangles, one emissive quad, mixed reflective walls) at
+    1920x1080, 4096 spp, 8 bounces: 8.5e9 samples."""
+    cfg = scenes.CONFIGS[2]
+    osc, hs = build_pair(*scenes.config_arrays(cfg))
+    st = _full_size_checks(gpu_ctx, hs, osc, camera, cfg, n_pixels=10)
+    assert st["rays_traced"] > 1.5 * st["samples"]
+
+
+def test_baseline_config4_at_full_size(gpu_ctx, camera):
+    """BASELINE.json configs[3]: synthetic 1 M-triangle mesh (height-19 BIH, traversal bound) at 3840x2160, 256 spp."""
+    cfg = scenes.CONFIGS[3]
+    osc, hs = build_pair(*scenes.config_arrays(cfg))
+    assert hs.n_tris > 990_000 and hs.stats()["height"] >= 18
+    _full_size_checks(gpu_ctx, hs, osc, camera, cfg, n_pixels=16)
+
+
+def test_baseline_config5_at_full_size(gpu_ctx, camera):
+    """BASELINE.json configs[4]: 10 M-triangle soup, every material fully reflective, 16 bounces, 3840x2160, 64 spp --
+    the incoherent-ray stress (480 MB of triangles; paths really bounce: more than 10 rays per sample)."""
+    cfg = scenes.CONFIGS[4]
+    osc, hs = build_pair(*scenes.config_arrays(cfg))
+    assert hs.n_tris == 10_000_000
+    st = _full_size_checks(gpu_ctx, hs, osc, camera, cfg, n_pixels=12)
+    assert st["rays_traced"] > 10 * st["samples"]
+    up = gpu_ctx.last_upload()
+    assert up["h2d_bytes"] > 480e6

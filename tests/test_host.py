@@ -121,7 +121,7 @@ def test_parser_error_behaviour(tmp_path):
 def test_objects_with_unknown_material_are_dropped_and_yz_swapped(tmp_path):
     obj = tmp_path / "s.obj"
     obj.write_text("mtllib m.sq\no A\nv 0 1 2\nv 1 0 0\nv 0 0 1\nusemtl M\ns off\nf 1 2 3\no B\nv 5 5 5\nusemtl Nope\nf 1 2 4\n")
-    (tmp_path / "m.sq").write_text("newmtl M\nreflective 0.25 .1 .2 .3\nemissive 2 1 1 1\n\nnewmtl Other\nreflective 0 0 0 0\nemissive 0 0 0 0\n")
+    (tmp_path / "m.sq").write_text("newmtl M\nreflective 0.25 0.1 0.2 0.3\nemissive 2 1 1 1\n\nnewmtl Other\nreflective 0 0 0 0\nemissive 0 0 0 0\n")
     hs = pysqt.HostScene.load(str(obj), str(tmp_path))
     osc = O.Scene.load(str(obj), str(tmp_path))
     v9, mi = hs.parsed_tris()
@@ -155,3 +155,22 @@ def test_cli_fails_loudly_without_gpu_or_runs(tmp_path):
     h = subprocess.run([exe, "--help"], capture_output=True, text=True)
     for flag in ("--samples", "--dimensions", "--savepath", "--objpath", "--camerapath", "--debug", "--debugpath", "--cast"):
         assert flag in h.stdout
+
+
+def test_obj_parser_is_as_strict_as_parsec_and_read(tmp_path):
+    """Obj.hs:96-147 through parsec + `read`: text starting with `s` that is neither `s on` nor `s off` is a parse error
+    (parsec's `string` consumes before it fails), `1.` / `.5` are `Prelude.read: no parse`; trailing input after the last
+    object is ignored (no `eof` in the reference) -- here with a warning."""
+    import pysqt
+    (tmp_path / "m.sq").write_text("newmtl A\nreflective 0.5 1 1 1\nemissive 0 0 0 0\n")
+    base = "mtllib m.sq\no X\nv 0 0 0\nv 1 0 0\nv 0 1 0\nusemtl A\n%sf 1 2 3\n"
+
+    def load(text):
+        (tmp_path / "s.obj").write_text(text)
+        return pysqt.HostScene.load(str(tmp_path / "s.obj"), str(tmp_path))
+    assert load(base % "s off\n").n_tris == 1 and load(base % "s on\n").n_tris == 1 and load(base % "").n_tris == 1
+    for bad in (base % "s 1\n", (base % "").replace("v 1 0 0", "v 1. 0 0"), (base % "").replace("v 1 0 0", "v .5 0 0"),
+                (base % "").replace("v 1 0 0", "v -.5 0 0")):
+        with pytest.raises(pysqt.SqtError, match="Irrefutable pattern"):
+            load(bad)
+    assert load(base % "" + "garbage\n").n_tris == 1
