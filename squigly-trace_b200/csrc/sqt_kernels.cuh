@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(128) k_intersect_batch(SceneView sc, const flo
     flush_stats(ds, st, cn, COUNT);
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
 struct DeviceAppend {
     unsigned long long *counter;
     int *list;
@@ -255,8 +257,8 @@ __global__ void __launch_bounds__(128, SQT_WL_MIN_BLOCKS) k_paths(SceneView sc, 
 // state lives in shared memory (structure of arrays, 16 words per ray; traversal stacks, per-path material lists and the
 // integrator state of a slot in global memory, one region per pool slot).  A ray waits in one of three queues (rings of
 // slot ids in shared memory, appended to with a ballot + popc at write-back, so there is no census and no gather):
-//   T  traversal steps (ST_DESC / ST_RET): a short burst of branch visits + stack pops; the ray's interval, child and best
-//      hit travel in registers, its origin / direction components are read from the pool by split axis (PoolRay)
+//   T  traversal steps (ST_DESC): a short burst of branch visits; the ray's interval and child travel in registers, its
+//      origin / direction components are read from the pool by split axis (PoolRay)
 //   L  leaf work (ST_ENTER / ST_LEAF): every gathered ray enters its leaf (record fetch + conservative culling), then the
 //      (ray, triangle) tests of ALL gathered rays are laid out consecutively and executed 32 per step, one test per lane,
 //      whichever lane gathered the ray -- any lane can read any ray from the pool -- and accepted hits are folded into
@@ -342,25 +344,24 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         const PoolRay ra(pool + slot, P);
         if (COUNT) { dbg_rounds[kind] += 1; dbg_sel[kind] += n_sel; }
         if (kind == KT) {
-            // ---- traversal steps: stack pops + branch visits
+            // ---- traversal steps: branch visits only.  Stack pops happen at the end of the leaf round (stage 3), so the rare
+            //      ray whose visit ends in ST_RET here (neither child box hit) simply queues for a leaf round with no leaf
+            //      work; the best hit is not touched by a visit and stays in the pool.
             uint32_t fl = 0u;
             L.stack = wstack + slot;
             if (act) {
                 L.child = PW(PF_CHILD, slot); L.tmin = u2f(PW(PF_TMIN, slot)); L.tmax = u2f(PW(PF_TMAX, slot));
-                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
                 fl = PW(PF_FLAGS, slot);
                 L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
             }
             for (int b = 0; b < tn.burst_t; ++b) {
-                if (COUNT) { dbg_ret[b < 7 ? b : 7] += __popc(__ballot_sync(FULL, L.state == ST_RET)); }
-                if (L.state == ST_RET) ret_step<P>(sc, L, ra);
                 if (COUNT) { dbg_desc[b < 7 ? b : 7] += __popc(__ballot_sync(FULL, L.state == ST_DESC)); }
                 if (L.state == ST_DESC) desc_step<COUNT, P>(sc, L, ra, &cn);
-                if (__popc(__ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET)) <= tn.t_leave) break;
+                if (__popc(__ballot_sync(FULL, L.state == ST_DESC)) <= tn.t_leave) break;
             }
             if (act) {
                 PW(PF_CHILD, slot) = L.child; PW(PF_TMIN, slot) = f2u(L.tmin); PW(PF_TMAX, slot) = f2u(L.tmax);
-                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
+                if (L.state == ST_RET) PW(PF_CTRI, slot) = 0xffffffffu;     // desc_step: the subtree returned Nothing
                 PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
             }
         } else if (kind == KL) {
@@ -439,16 +440,27 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 __syncwarp(FULL);
                 const int start = incl - c;
                 int started = 0;                                            // owners whose range starts before `base` (warp-uniform)
-                for (int base = 0; base < total; base += 32) {
-                    const int pr = base + lane;
+                // the mapping of a chunk is computed one iteration ahead, and the chunk's triangles are prefetched into L1
+                // while the previous chunk is tested
+                auto map_chunk = [&](int base, int &own_o, uint32_t &idx_o, int &oslot_o) {
                     const unsigned rel = (unsigned)(start - base);
                     const unsigned sm = __reduce_or_sync(FULL, (c > 0 && rel < 32u) ? (1u << rel) : 0u);
                     int k = started + __popc(sm & (0xffffffffu >> (31 - lane))) - 1;
                     started += __popc(sm);
-                    if (pr >= total) k = 0;
-                    const int own = (int)own_tab[k];
-                    const uint32_t idx = own_tab[32 + k] - (uint32_t)pr;
-                    const int oslot = (int)lane_slot[own];
+                    if (base + lane >= total) k = 0;
+                    own_o = (int)own_tab[k];
+                    idx_o = own_tab[32 + k] - (uint32_t)(base + lane);
+                    oslot_o = (int)lane_slot[own_o];
+                    if (base + lane < total) prefetch_l1(sc.tris + 3 * (size_t)idx_o);
+                };
+                int own_n = 0, oslot_n = 0;
+                uint32_t idx_n = 0u;
+                map_chunk(0, own_n, idx_n, oslot_n);
+                for (int base = 0; base < total; base += 32) {
+                    const int pr = base + lane;
+                    const int own = own_n, oslot = oslot_n;
+                    const uint32_t idx = idx_n;
+                    if (base + 32 < total) map_chunk(base + 32, own_n, idx_n, oslot_n);
                     bool pass = false;
                     if (pr < total) {
                         const TriData d = tri_load(sc, idx);
@@ -515,8 +527,8 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         }
         // ---- append every served ray to the queue of the step it needs next
         {
-            // ST_DONE 0 -> KR, ST_DESC 1 -> KT, ST_LEAF 2 -> KL, ST_RET 3 -> KT, ST_EXIT 4 -> none, ST_ENTER 5 -> KL
-            const int nk = act ? (int)((0x130102u >> (4 * L.state)) & 3u) : KNONE;
+            // ST_DONE 0 -> KR, ST_DESC 1 -> KT, ST_LEAF 2 -> KL, ST_RET 3 -> KL, ST_EXIT 4 -> none, ST_ENTER 5 -> KL
+            const int nk = act ? (int)((0x131102u >> (4 * L.state)) & 3u) : KNONE;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const unsigned m = __ballot_sync(FULL, nk == k);
