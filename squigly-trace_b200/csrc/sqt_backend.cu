@@ -86,7 +86,7 @@ static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v
 // Environment knobs (development only; they change scheduling, never a result).  Malformed values are ignored and every
 // value is clamped to a range in which the persistent kernels are guaranteed to make progress.
 static void read_env_tuning(sqt_ctx *c) {
-    if (const char *t = getenv("SQT_POOL")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 4) c->pool_k = (int)k; }
+    if (const char *t = getenv("SQT_POOL")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 4) c->pool_k = k == 3 ? 4 : (int)k; }      // rays per warp = 32 * K, K a power of two
     if (const char *t = getenv("SQT_POOL_BLOCKS")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 32) c->pool_blocks = (int)k; }
     if (const char *t = getenv("SQT_POOL_TUNE")) {       // "burst_t,t_leave,c_min"
         int a, b, cm;
@@ -405,7 +405,7 @@ static int persistent_grid(sqt_ctx *ctx, K kernel, long long nwork) {
 struct PoolPlan { int grid = 0; size_t smem = 0; int depth = 1, pm_stride = 8; };
 template <bool COUNT, int K>
 static int pool_step(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems, bool launch) {
-    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 3 * (32 * K / 4) + 64 + 96) * sizeof(uint32_t);
+    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 3 * (32 * K) / 4 + 64 + 8 + 8 + 32) * sizeof(uint32_t);
     auto kern = k_paths_pool<COUNT, K>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -447,7 +447,6 @@ static int pool_step_k(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd,
     switch (ctx->pool_k) {
     case 1: return pool_step<COUNT, 1>(ctx, d, rd, round, nitems, launch);
     case 2: return pool_step<COUNT, 2>(ctx, d, rd, round, nitems, launch);
-    case 3: return pool_step<COUNT, 3>(ctx, d, rd, round, nitems, launch);
     default: return pool_step<COUNT, 4>(ctx, d, rd, round, nitems, launch);
     }
 }

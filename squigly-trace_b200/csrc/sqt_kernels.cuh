@@ -287,68 +287,74 @@ template <bool COUNT, int K>
 __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, PoolTune tn,
                                                     float4 *__restrict__ gstack, uint16_t *__restrict__ gpm, uint4 *__restrict__ gpath, int stack_depth, int pm_stride) {
     extern __shared__ uint32_t pool_smem[];
-    constexpr int P = 32 * K;
-    constexpr int WARP_WORDS = P * PF_WORDS + 3 * (P / 4) + 64 + 96;
+    constexpr int P = 32 * K;                     // rays per warp (a power of two)
+    constexpr int PT = 4 * P;                     // pool slots of the CTA: slot g = warp * P + s, and g is what the queues hold,
+                                                  // so the hot accesses index CTA-wide arrays by a value the lane already has
+                                                  // (no per-warp base address to rematerialise)
+    // per-warp scratch, kept small on purpose: 8 CTAs x (pool + scratch + 1 KB) must stay within the 164 KB shared-memory
+    // carve-out, the next one (196 KB) would leave 32 KB instead of 64 KB of L1 for triangles, nodes and stacks
+    constexpr int AUX_WORDS = 3 * P / 4 + 64 + 8 + 8 + 32;
     const unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *pool = pool_smem + warp * WARP_WORDS;
-    uint8_t *queue = (uint8_t *)(pool + P * PF_WORDS);                          // queue[k * P + i], k = KT, KL, KR
-    uint32_t *survivors = pool + P * PF_WORDS + 3 * (P / 4);                    // ring of 64 (triangle | gathering lane << 27)
-    uint32_t *lane_slot = survivors + 64;                                       // leaf round: the pool slot each lane gathered
-    uint32_t *own_tab = lane_slot + 32;                                         // leaf round: per owner rank (lane, triangle base)
-    const int gslot0 = (int)((blockIdx.x * (blockDim.x >> 5) + warp) * P);     // < 2^31: at most a few hundred thousand pool slots exist
-    float4 *wstack = gstack + (size_t)gslot0 * (size_t)stack_depth;            // entry e of slot s at wstack[e * P + s]
-#define PW(f, slot) pool[(f) * P + (slot)]
+    const int wbase = warp * P;
+    uint32_t *pool = pool_smem;                                                 // word f of slot g at pool[f * PT + g]
+    uint32_t *aux = pool_smem + PT * PF_WORDS + warp * AUX_WORDS;
+    uint8_t *queue = (uint8_t *)aux;                                            // queue[k * P + i], k = KT, KL, KR: rings of slot ids (g - wbase)
+    uint32_t *survivors = aux + 3 * P / 4;                                      // ring of 64 (triangle | gathering lane << 27)
+    uint8_t *lane_slot = (uint8_t *)(survivors + 64);                           // leaf round: the slot (g - wbase) each lane gathered
+    uint8_t *own_lane = lane_slot + 32;                                         // leaf round, per owner rank: its lane ...
+    uint32_t *own_tri = survivors + 64 + 16;                                    // ... and triangle of its test 0 + that test's position
+    const int gbase = (int)(blockIdx.x * PT);                                   // global slot = gbase + g (< 2^31: a few hundred thousand exist)
+    float4 *cstack = gstack + (size_t)gbase * (size_t)stack_depth;              // entry e of slot g at cstack[e * PT + g]
+#define PW(f, g) pool[(f) * PT + (g)]
     Counters cn = {};
     PathStats st = {0, 0, 0};
     if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
     DeviceFetch fetch = {&ds->work_next[round], rd.n_slots << rd.log2_s};
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int slot = lane + 32 * k;
+        const int slot = wbase + lane + 32 * k;
         PW(PF_FLAGS, slot) = (uint32_t)ST_DONE;
         PW(PF_CTRI, slot) = 0xffffffffu;
-        queue[KR * P + slot] = (uint8_t)slot;
-        gpath[2 * (gslot0 + slot)] = make_uint4(0u, 0u, 0u, 0u);
-        gpath[2 * (gslot0 + slot) + 1] = make_uint4(0u, 0u, 0u, 0u);      // saved_j = -1 (stored +1), any_emit = in_flight = false
+        queue[KR * P + lane + 32 * k] = (uint8_t)(lane + 32 * k);
+        gpath[2 * (gbase + slot)] = make_uint4(0u, 0u, 0u, 0u);
+        gpath[2 * (gbase + slot) + 1] = make_uint4(0u, 0u, 0u, 0u);      // saved_j = -1 (stored +1), any_emit = in_flight = false
     }
     __syncwarp(FULL);
     const unsigned lt_mask = (1u << lane) - 1u;
-    int q_head[3] = {0, 0, 0}, q_cnt[3] = {0, 0, P};                       // warp-uniform
+    // queue state, warp-uniform, one byte per kind: ring head (< P) and fill (<= P <= 128)
+    unsigned q_head = 0u, q_cnt = (unsigned)P << (8 * KR);
     unsigned long long dbg_rounds[3] = {0, 0, 0}, dbg_sel[3] = {0, 0, 0}, dbg_desc[8] = {}, dbg_ret[8] = {}, dbg_leaf[4] = {};
     for (;;) {
         // ---- pick the longest queue (regeneration only in batches, or when nothing else can run)
-        const int c_r = (q_cnt[KR] >= tn.c_min || (q_cnt[KT] | q_cnt[KL]) == 0) ? q_cnt[KR] : 0;
-        int kind = KL, best = q_cnt[KL];
-        if (q_cnt[KT] > best) { kind = KT; best = q_cnt[KT]; }
+        const int n_t = (int)(q_cnt & 0xffu), n_l = (int)((q_cnt >> 8) & 0xffu), n_r = (int)(q_cnt >> 16);
+        const int c_r = (n_r >= tn.c_min || (q_cnt & 0xffffu) == 0u) ? n_r : 0;
+        int kind = KL, best = n_l;
+        if (n_t > best) { kind = KT; best = n_t; }
         if (c_r > best) { kind = KR; best = c_r; }
         if (best == 0) break;                                               // every slot is ST_EXIT
         // ---- pop up to 32 rays of that kind onto the lanes
         const int n_sel = best < 32 ? best : 32;
         const bool act = lane < n_sel;
-        int slot = 0;
+        int slot = wbase;                                                   // (inactive lanes: any valid slot of this warp)
         {
-            const int h = kind == KT ? q_head[KT] : (kind == KL ? q_head[KL] : q_head[KR]);
-            int pos = h + lane;
-            if (pos >= P) pos -= P;
-            if (act) slot = (int)queue[kind * P + pos];
-            int nh = h + n_sel;
-            if (nh >= P) nh -= P;
-            if (kind == KT) { q_head[KT] = nh; q_cnt[KT] -= n_sel; }
-            else if (kind == KL) { q_head[KL] = nh; q_cnt[KL] -= n_sel; }
-            else { q_head[KR] = nh; q_cnt[KR] -= n_sel; }
+            const int sh = 8 * kind;
+            const unsigned h = (q_head >> sh) & 0xffu;
+            if (act) slot = wbase + (int)queue[kind * P + ((h + lane) & (P - 1))];
+            q_head = (q_head & ~(0xffu << sh)) | (((h + n_sel) & (P - 1)) << sh);
+            q_cnt -= (unsigned)n_sel << sh;
         }
         TravLane L;
         L.stack = nullptr;
         L.state = ST_EXIT;
-        const PoolRay ra(pool + slot, P);
+        const PoolRay ra(pool + slot, PT);
         if (COUNT) { dbg_rounds[kind] += 1; dbg_sel[kind] += n_sel; }
         if (kind == KT) {
             // ---- traversal steps: branch visits only.  Stack pops happen at the end of the leaf round (stage 3), so the rare
             //      ray whose visit ends in ST_RET here (neither child box hit) simply queues for a leaf round with no leaf
             //      work; the best hit is not touched by a visit and stays in the pool.
             uint32_t fl = 0u;
-            L.stack = wstack + slot;
+            L.stack = cstack + slot;
             if (act) {
                 L.child = PW(PF_CHILD, slot); L.tmin = u2f(PW(PF_TMIN, slot)); L.tmax = u2f(PW(PF_TMAX, slot));
                 fl = PW(PF_FLAGS, slot);
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             }
             for (int b = 0; b < tn.burst_t; ++b) {
                 if (COUNT) { dbg_desc[b < 7 ? b : 7] += __popc(__ballot_sync(FULL, L.state == ST_DESC)); }
-                if (L.state == ST_DESC) desc_step<COUNT, P>(sc, L, ra, &cn);
+                if (L.state == ST_DESC) desc_step<COUNT, PT>(sc, L, ra, &cn);
                 if (__popc(__ballot_sync(FULL, L.state == ST_DESC)) <= tn.t_leave) break;
             }
             if (act) {
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             uint32_t fl = 0u;
             uint32_t first = 0u;
             int rem = 0;                                                    // triangles of this lane's ray still to test
-            lane_slot[lane] = (uint32_t)slot;
+            lane_slot[lane] = (uint8_t)(slot & (P - 1));
             if (act) {
                 fl = PW(PF_FLAGS, slot);
                 L.child = PW(PF_CHILD, slot);
@@ -392,13 +398,13 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             int n_surv = 0, surv_head = 0;                                  // warp-uniform
             auto run_survivors = [&](int n) {
                 const uint32_t e = lane < n ? survivors[(surv_head + lane) & 63] : 0u;
-                const int oslot = (int)lane_slot[e >> 27];
+                const int oslot = wbase + (int)lane_slot[e >> 27];
                 const uint32_t idx = e & kLeafFirstMask;
                 bool hit = false;
                 float t = 0.0f, dist = 0.0f;
                 if (lane < n) {
                     const TriData d = tri_load(sc, idx);
-                    const Ray r = PoolRay(pool + oslot, P).ray();
+                    const Ray r = PoolRay(pool + oslot, PT).ray();
                     int stage;
                     hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
                     if (COUNT) { cn.mt_pass_v += stage >= 3; cn.mt_accept += stage >= 4; }
@@ -434,8 +440,8 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 const unsigned om = __ballot_sync(FULL, c > 0);
                 if (c > 0) {
                     const int rank = __popc(om & lt_mask);
-                    own_tab[rank] = (uint32_t)lane;
-                    own_tab[32 + rank] = (uint32_t)((int)first + rem - 1 + (incl - c));      // triangle of test p of this ray = that - p
+                    own_lane[rank] = (uint8_t)lane;
+                    own_tri[rank] = (uint32_t)((int)first + rem - 1 + (incl - c));           // triangle of test p of this ray = that - p
                 }
                 __syncwarp(FULL);
                 const int start = incl - c;
@@ -448,9 +454,9 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                     int k = started + __popc(sm & (0xffffffffu >> (31 - lane))) - 1;
                     started += __popc(sm);
                     if (base + lane >= total) k = 0;
-                    own_o = (int)own_tab[k];
-                    idx_o = own_tab[32 + k] - (uint32_t)(base + lane);
-                    oslot_o = (int)lane_slot[own_o];
+                    own_o = (int)own_lane[k];
+                    idx_o = own_tri[k] - (uint32_t)(base + lane);
+                    oslot_o = wbase + (int)lane_slot[own_o];
                     if (base + lane < total) prefetch_l1(sc.tris + 3 * (size_t)idx_o);
                 };
                 int own_n = 0, oslot_n = 0;
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                     bool pass = false;
                     if (pr < total) {
                         const TriData d = tri_load(sc, idx);
-                        const Ray r = PoolRay(pool + oslot, P).ray();
+                        const Ray r = PoolRay(pool + oslot, PT).ray();
                         int stage;
                         pass = moller_trumbore_au(d.a0, d.a1, d.a2, r, stage);
                         if (COUNT) { cn.mt_pass_a += stage >= 1; cn.mt_pass_u += stage >= 2; }
@@ -481,13 +487,13 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             // Stage 3: every gathered ray now holds the result of its leaf (or Nothing, if the leaf was culled or empty):
             // pop its stack right here, with all gathered lanes, instead of in a traversal round -- a third of the rays go
             // straight on to another leaf (the far child) or are finished and never need a traversal round in between.
-            L.stack = wstack + slot;
+            L.stack = cstack + slot;
             if (act) {
                 L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
                 L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
                 L.tmin = 0.0f; L.tmax = 0.0f; L.child = 0u;
                 L.state = ST_RET;
-                ret_step<P>(sc, L, ra);
+                ret_step<PT>(sc, L, ra);
                 PW(PF_CHILD, slot) = L.child; PW(PF_TMIN, slot) = f2u(L.tmin); PW(PF_TMAX, slot) = f2u(L.tmax);
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
                 PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
@@ -497,7 +503,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             //      gathered lanes together (path_regen_warp)
             PathRay q;
             path_ray_init(q);
-            uint4 *gp = gpath + 2 * (gslot0 + slot);
+            uint4 *gp = gpath + 2 * (gbase + slot);
             L.dfx = L.dfy = L.dfz = 0.0f; L.child = 0u; L.tmin = 0.0f; L.tmax = 0.0f; L.i = 0; L.sp = 0; L.safe = true; L.sgn = 0u;
             L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
             L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 q.saved_r = u2f(g1.x); q.saved_j = (int)(pf & 0xffffu) - 1;
                 q.any_emit = ((pf >> 16) & 1u) != 0u; q.in_flight = ((pf >> 17) & 1u) != 0u;
             }
-            path_regen_warp<COUNT>(sc, p, rd, fetch, st, q, gpm + (size_t)(gslot0 + slot) * (size_t)pm_stride, L, &cn, act);
+            path_regen_warp<COUNT>(sc, p, rd, fetch, st, q, gpm + (size_t)(gbase + slot) * (size_t)pm_stride, L, &cn, act);
             if (act) {
                 PW(PF_OX, slot) = f2u(L.r.ox); PW(PF_OY, slot) = f2u(L.r.oy); PW(PF_OZ, slot) = f2u(L.r.oz);
                 PW(PF_DX, slot) = f2u(L.r.dx); PW(PF_DY, slot) = f2u(L.r.dy); PW(PF_DZ, slot) = f2u(L.r.dz);
@@ -525,24 +531,23 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 gp[1] = make_uint4(f2u(q.saved_r), (uint32_t)(q.saved_j + 1) | (q.any_emit ? 0x10000u : 0u) | (q.in_flight ? 0x20000u : 0u), 0u, 0u);
             }
         }
-        // ---- append every served ray to the queue of the step it needs next
+        // ---- append every served ray to the queue of the step it needs next: lanes with the same destination find
+        //      each other with one MATCH, the three fills grow by one packed REDUX
         {
             // ST_DONE 0 -> KR, ST_DESC 1 -> KT, ST_LEAF 2 -> KL, ST_RET 3 -> KL, ST_EXIT 4 -> none, ST_ENTER 5 -> KL
             const int nk = act ? (int)((0x131102u >> (4 * L.state)) & 3u) : KNONE;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const unsigned m = __ballot_sync(FULL, nk == k);
-                if (nk == k) {
-                    int pos = q_head[k] + q_cnt[k] + __popc(m & lt_mask);
-                    if (pos >= P) pos -= P;
-                    queue[k * P + pos] = (uint8_t)slot;
-                }
-                q_cnt[k] += __popc(m);
+            const unsigned same = __match_any_sync(FULL, nk);
+            const unsigned add = __reduce_add_sync(FULL, nk < KNONE ? (1u << (8 * nk)) : 0u);
+            if (nk < KNONE) {
+                const unsigned tail = ((q_head + q_cnt) >> (8 * nk)) & 0xffu;      // per byte: head < P, fill <= P, no carry
+                queue[nk * P + ((tail + __popc(same & lt_mask)) & (P - 1))] = (uint8_t)(slot & (P - 1));
             }
+            q_cnt += add;
         }
         __syncwarp(FULL);
     }
 #undef PW
+    (void)gbase;
     if (COUNT && lane == 0) {
         for (int k = 0; k < 3; ++k) { atomicAdd(&ds->dbg[k], dbg_rounds[k]); atomicAdd(&ds->dbg[3 + k], dbg_sel[k]); }
         for (int k = 0; k < 8; ++k) { atomicAdd(&ds->dbg[8 + k], dbg_desc[k]); atomicAdd(&ds->dbg[16 + k], dbg_ret[k]); }

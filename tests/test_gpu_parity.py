@@ -297,7 +297,7 @@ def test_many_sample_rounds_are_bit_identical(host_scene, camera, monkeypatch):
     assert np.array_equal(bits(a["accum"]), bits(b["accum"])) and np.array_equal(a["rgb8"], b["rgb8"])
 
 
-@pytest.mark.parametrize("pool", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("pool", ["0", "1", "2", "4"])
 def test_every_path_kernel_scheduler_is_bit_exact(host_scene, oracle_scene, camera, monkeypatch, pool):
     """SQT_POOL selects how rays are scheduled onto lanes (0: one ray per lane, warp-synchronous phases; K: ray pools of
     32*K rays per warp in shared memory).  Scheduling must never change a result."""
