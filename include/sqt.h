@@ -71,8 +71,9 @@ typedef struct sqt_material {
 } sqt_material;                          /* 32 B */
 
 /* EXTENSION (named by the north star; the reference has no sphere primitive or syntax, so the semantics are this
- * library's own and are restated in oracle/oracle.c): analytic, double-sided spheres tested after the BIH for
- * every ray; the closest of the BIH hit and the sphere hits wins, earlier candidates win ties.  In tri_out a
+ * library's own and are restated in oracle/oracle.c): analytic, double-sided spheres; a ray's result is the closest of
+ * the BIH hit and all sphere hits, earlier candidates of the list [BIH hit, sphere 0, sphere 1, ...] win ties.  (The
+ * library finds the candidate spheres through a hierarchy of its own, see SQT_OPT_SPHERE_BVH.)  In tri_out a
  * sphere k is reported as n_tris + k. */
 typedef struct sqt_sphere {
     float center[3];
@@ -196,6 +197,10 @@ int sqt_measure_l2_bandwidth(sqt_ctx *ctx, double *gb_per_s);    /* L2-resident 
 /* options: SQT_OPT_LEAF_CULL (default 1) -- skip leaves whose conservatively enlarged tight box the ray
  * misses.  Exact; 0 reproduces the reference's triangle-test count one for one. */
 #define SQT_OPT_LEAF_CULL 1
+/* SQT_OPT_SPHERE_BVH (default 1) -- extension: find the spheres a ray can hit through a bounding-volume hierarchy built at
+ * sqt_upload_spheres instead of testing every sphere for every ray.  Exact (same closest surface, same tie-break); 0
+ * keeps the literal definition. */
+#define SQT_OPT_SPHERE_BVH 2
 int sqt_set_option(sqt_ctx *ctx, int option, int value);
 
 /* introspection used by tests */

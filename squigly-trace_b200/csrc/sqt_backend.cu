@@ -31,6 +31,7 @@ struct sqt_ctx {
     bool has_scene = false;
     SceneView sc = {};
     float4 *d_nodes = nullptr, *d_boxes = nullptr, *d_tris = nullptr, *d_mats = nullptr, *d_leaves = nullptr, *d_spheres = nullptr;
+    float4 *d_sph_nodes = nullptr; uint32_t *d_sph_order = nullptr; int sphere_bvh = 1;      // extension: hierarchy over the spheres
     uint2 *d_ranges = nullptr;          // (first, count) per leaf, input of k_leaf_records
     uint32_t *d_flag = nullptr;         // material check result
     size_t cap_branches = 0, cap_leaves = 0, cap_tris = 0, cap_mats = 0;     // allocation sizes (records), reused across uploads
@@ -135,8 +136,8 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
 }
 
 static void free_scene(sqt_ctx *c) {
-    cudaFree(c->d_nodes); cudaFree(c->d_boxes); cudaFree(c->d_tris); cudaFree(c->d_mats); cudaFree(c->d_leaves); cudaFree(c->d_spheres); cudaFree(c->d_ranges);
-    c->d_nodes = c->d_boxes = c->d_tris = c->d_mats = c->d_leaves = c->d_spheres = nullptr; c->d_ranges = nullptr; c->has_scene = false;
+    cudaFree(c->d_nodes); cudaFree(c->d_boxes); cudaFree(c->d_tris); cudaFree(c->d_mats); cudaFree(c->d_leaves); cudaFree(c->d_spheres); cudaFree(c->d_sph_nodes); cudaFree(c->d_sph_order); cudaFree(c->d_ranges);
+    c->d_nodes = c->d_boxes = c->d_tris = c->d_mats = c->d_leaves = c->d_spheres = c->d_sph_nodes = nullptr; c->d_sph_order = nullptr; c->d_ranges = nullptr; c->has_scene = false;
     c->cap_branches = c->cap_leaves = c->cap_tris = c->cap_mats = 0;
 }
 
@@ -341,16 +342,37 @@ extern "C" int sqt_upload_spheres(sqt_ctx *ctx, const sqt_sphere *sp, uint32_t n
         ds[2 * k] = make_float4(sp[k].center[0], sp[k].center[1], sp[k].center[2], sp[k].radius);
         ds[2 * k + 1] = make_float4(u2f(sp[k].material), 0.0f, 0.0f, 0.0f);
     }
-    cudaFree(ctx->d_spheres); ctx->d_spheres = nullptr;
+    cudaFree(ctx->d_spheres); cudaFree(ctx->d_sph_nodes); cudaFree(ctx->d_sph_order);
+    ctx->d_spheres = nullptr; ctx->d_sph_nodes = nullptr; ctx->d_sph_order = nullptr;
+    ctx->sc.spheres = nullptr; ctx->sc.sph_nodes = nullptr; ctx->sc.sph_order = nullptr; ctx->sc.n_spheres = 0;
+    if (n == 0) return SQT_OK;
     CU(cudaMalloc(&ctx->d_spheres, ds.size() * sizeof(float4)));
     CU(cudaMemcpy(ctx->d_spheres, ds.data(), ds.size() * sizeof(float4), cudaMemcpyHostToDevice));
     ctx->sc.spheres = ctx->d_spheres; ctx->sc.n_spheres = n;
+    // a hierarchy over the spheres (sphere_step): only for finite, moderate coordinates -- the culling bound assumes no overflow
+    bool tame = ctx->sphere_bvh != 0;
+    for (uint32_t k = 0; k < n && tame; ++k)
+        for (int q = 0; q < 4; ++q) { const float v = q < 3 ? sp[k].center[q] : sp[k].radius; if (!(fabsf(v) < 1.0e12f)) tame = false; }
+    if (tame) {
+        SphereBvh bvh;
+        build_sphere_bvh(sp, n, bvh);
+        CU(cudaMalloc(&ctx->d_sph_nodes, bvh.nodes.size() * sizeof(float4)));
+        CU(cudaMalloc(&ctx->d_sph_order, bvh.order.size() * sizeof(uint32_t)));
+        CU(cudaMemcpy(ctx->d_sph_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_sph_order, bvh.order.data(), bvh.order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        ctx->sc.sph_nodes = ctx->d_sph_nodes; ctx->sc.sph_order = ctx->d_sph_order;
+    }
     return SQT_OK;
 }
 
 extern "C" int sqt_set_option(sqt_ctx *ctx, int option, int value) {
     if (!ctx) return SQT_E_INVALID;
     if (option == SQT_OPT_LEAF_CULL) { ctx->leaf_cull = value ? 1 : 0; ctx->sc.leaf_cull = (uint32_t)ctx->leaf_cull; return SQT_OK; }
+    if (option == SQT_OPT_SPHERE_BVH) {          // takes effect at the next sqt_upload_spheres; 0 = test every sphere for every ray (the definition)
+        ctx->sphere_bvh = value ? 1 : 0;
+        if (!value) { ctx->sc.sph_nodes = nullptr; ctx->sc.sph_order = nullptr; }
+        return SQT_OK;
+    }
     return fail(ctx, SQT_E_INVALID, "unknown option %d", option);
 }
 
@@ -405,7 +427,7 @@ static int persistent_grid(sqt_ctx *ctx, K kernel, long long nwork) {
 struct PoolPlan { int grid = 0; size_t smem = 0; int depth = 1, pm_stride = 8; };
 template <bool COUNT, int K>
 static int pool_step(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, int round, long long nitems, bool launch) {
-    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 3 * (32 * K) / 4 + 64 + 8 + 8 + 32) * sizeof(uint32_t);
+    const size_t smem = (size_t)4 * (32 * K * PF_WORDS + 4 * (32 * K) / 4 + 64 + 8 + 8 + 32) * sizeof(uint32_t);
     auto kern = k_paths_pool<COUNT, K>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

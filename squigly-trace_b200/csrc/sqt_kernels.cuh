@@ -140,6 +140,11 @@ __device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Coun
     L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
     const LaneRay ra(L);
     for (;;) {
+        // ---- (extension) rays whose BIH part is finished fold in the analytic spheres
+        if (__any_sync(FULL, L.state == ST_SPH)) {
+            if (L.state == ST_SPH) sphere_step(sc, L, ra);
+            __syncwarp(FULL);
+        }
         // ---- regeneration
         const unsigned m_done = __ballot_sync(FULL, L.state == ST_DONE);
         const unsigned m_busy = __ballot_sync(FULL, L.state == ST_DESC || L.state == ST_RET || L.state == ST_LEAF || L.state == ST_ENTER);
@@ -281,7 +286,7 @@ struct PoolTune { int burst_t, t_leave, c_min; };
 // PF_FLAGS = state | safe << 8 | sgn << 16 | sp << 24.
 enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_TMIN, PF_TMAX, PF_CTRI, PF_CT, PF_CDIST,
        PF_FLAGS, PF_WORDS };
-enum { KT = 0, KL = 1, KR = 2, KNONE = 3 };
+enum { KT = 0, KL = 1, KR = 2, KS = 3, KNONE = 4 };
 
 template <bool COUNT, int K>
 __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneView sc, RenderParams p, RoundInfo rd, int round, DeviceStats *ds, PoolTune tn,
@@ -293,14 +298,14 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                                                   // (no per-warp base address to rematerialise)
     // per-warp scratch, kept small on purpose: 8 CTAs x (pool + scratch + 1 KB) must stay within the 164 KB shared-memory
     // carve-out, the next one (196 KB) would leave 32 KB instead of 64 KB of L1 for triangles, nodes and stacks
-    constexpr int AUX_WORDS = 3 * P / 4 + 64 + 8 + 8 + 32;
+    constexpr int AUX_WORDS = 4 * P / 4 + 64 + 8 + 8 + 32;
     const unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wbase = warp * P;
     uint32_t *pool = pool_smem;                                                 // word f of slot g at pool[f * PT + g]
     uint32_t *aux = pool_smem + PT * PF_WORDS + warp * AUX_WORDS;
-    uint8_t *queue = (uint8_t *)aux;                                            // queue[k * P + i], k = KT, KL, KR: rings of slot ids (g - wbase)
-    uint32_t *survivors = aux + 3 * P / 4;                                      // ring of 64 (triangle | gathering lane << 27)
+    uint8_t *queue = (uint8_t *)aux;                                            // queue[k * P + i], k = KT, KL, KR, KS: rings of slot ids (g - wbase)
+    uint32_t *survivors = aux + 4 * P / 4;                                      // ring of 64 (triangle | gathering lane << 27)
     uint8_t *lane_slot = (uint8_t *)(survivors + 64);                           // leaf round: the slot (g - wbase) each lane gathered
     uint8_t *own_lane = lane_slot + 32;                                         // leaf round, per owner rank: its lane ...
     uint32_t *own_tri = survivors + 64 + 16;                                    // ... and triangle of its test 0 + that test's position
@@ -321,16 +326,18 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         gpath[2 * (gbase + slot) + 1] = make_uint4(0u, 0u, 0u, 0u);      // saved_j = -1 (stored +1), any_emit = in_flight = false
     }
     __syncwarp(FULL);
-    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     // queue state, warp-uniform, one byte per kind: ring head (< P) and fill (<= P <= 128)
-    unsigned q_head = 0u, q_cnt = (unsigned)P << (8 * KR);
+    unsigned q_head = 0u, q_cnt = (unsigned)P << (8 * KR);     // (P = 128 fills its byte exactly: the top byte, KS, never holds more than P)
     unsigned long long dbg_rounds[3] = {0, 0, 0}, dbg_sel[3] = {0, 0, 0}, dbg_desc[8] = {}, dbg_ret[8] = {}, dbg_leaf[4] = {};
     for (;;) {
         // ---- pick the longest queue (regeneration only in batches, or when nothing else can run)
-        const int n_t = (int)(q_cnt & 0xffu), n_l = (int)((q_cnt >> 8) & 0xffu), n_r = (int)(q_cnt >> 16);
-        const int c_r = (n_r >= tn.c_min || (q_cnt & 0xffffu) == 0u) ? n_r : 0;
+        const int n_t = (int)(q_cnt & 0xffu), n_l = (int)((q_cnt >> 8) & 0xffu), n_r = (int)((q_cnt >> 16) & 0xffu), n_s = (int)(q_cnt >> 24);
+        const int c_r = (n_r >= tn.c_min || (q_cnt & 0xff00ffffu) == 0u) ? n_r : 0;
         int kind = KL, best = n_l;
         if (n_t > best) { kind = KT; best = n_t; }
+        if (n_s > best) { kind = KS; best = n_s; }
         if (c_r > best) { kind = KR; best = c_r; }
         if (best == 0) break;                                               // every slot is ST_EXIT
         // ---- pop up to 32 rays of that kind onto the lanes
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         L.stack = nullptr;
         L.state = ST_EXIT;
         const PoolRay ra(pool + slot, PT);
-        if (COUNT) { dbg_rounds[kind] += 1; dbg_sel[kind] += n_sel; }
+        if (COUNT && kind < 3) { dbg_rounds[kind] += 1; dbg_sel[kind] += n_sel; }
         if (kind == KT) {
             // ---- traversal steps: branch visits only.  Stack pops happen at the end of the leaf round (stage 3), so the rare
             //      ray whose visit ends in ST_RET here (neither child box hit) simply queues for a leaf round with no leaf
@@ -498,6 +505,16 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
                 PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
             }
+        } else if (kind == KS) {
+            // ---- (extension) fold the analytic spheres into the BIH result of every gathered ray (sphere_step)
+            if (act) {
+                const uint32_t fl = PW(PF_FLAGS, slot);
+                L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
+                L.state = ST_SPH;
+                sphere_step(sc, L, ra);
+                PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
+                PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)L.state;
+            }
         } else {
             // ---- regeneration: consume the finished hit, shade, start the next ray (or the next sample); staged, all
             //      gathered lanes together (path_regen_warp)
@@ -534,8 +551,8 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         // ---- append every served ray to the queue of the step it needs next: lanes with the same destination find
         //      each other with one MATCH, the three fills grow by one packed REDUX
         {
-            // ST_DONE 0 -> KR, ST_DESC 1 -> KT, ST_LEAF 2 -> KL, ST_RET 3 -> KL, ST_EXIT 4 -> none, ST_ENTER 5 -> KL
-            const int nk = act ? (int)((0x131102u >> (4 * L.state)) & 3u) : KNONE;
+            // ST_DONE 0 -> KR, ST_DESC 1 -> KT, ST_LEAF 2 -> KL, ST_RET 3 -> KL, ST_EXIT 4 -> none, ST_ENTER 5 -> KL, ST_SPH 6 -> KS
+            const int nk = act ? (int)((0x3141102u >> (4 * L.state)) & 7u) : KNONE;
             const unsigned same = __match_any_sync(FULL, nk);
             const unsigned add = __reduce_add_sync(FULL, nk < KNONE ? (1u << (8 * nk)) : 0u);
             if (nk < KNONE) {

@@ -7,6 +7,7 @@
 // caller (device kernels in the product, make_leaf_record on the host in tests/emu).  Shared by sqt_backend.cu (the
 // product) and tests/emu (host build of the kernel logic).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -143,6 +144,53 @@ inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, st
     out.nodes.swap(dn); out.boxes.swap(db); out.mats.swap(dm);
     out.n_branches = n_br; out.n_slow = n_slow; out.height = height; out.terminate_on_black_ok = tob; out.planes_finite = planes_finite;
     return SQT_OK;
+}
+
+// ---- extension: bounding-volume hierarchy over the analytic spheres (sphere_step in sqt_core.cuh) -----------------
+// Median split of the centres along the longest axis of their bounds, at most 4 spheres per leaf, pre-order numbering
+// (root = 0): depth <= ceil(log2(n / 2)) + 1 <= 27 for the 2^27 surfaces the indices allow.  Node = 2 x float4:
+// (lo.xyz, hi.x) (hi.yz, a, b); interior a = low child | split axis << 30, b = high child; leaf a = first entry of `order`,
+// b = count | kLeaf.  Boxes bound centre +- radius * (1 + 2^-19), rounded outwards (the radius term of the culling bound).
+struct SphereBvh { std::vector<float4> nodes; std::vector<uint32_t> order; };
+inline void build_sphere_bvh(const sqt_sphere *sp, uint32_t n, SphereBvh &out) {
+    out.nodes.clear(); out.order.resize(n);
+    for (uint32_t i = 0; i < n; ++i) out.order[i] = i;
+    if (n == 0) return;
+    struct Job { uint32_t lo, hi, node; };
+    std::vector<Job> todo;
+    out.nodes.resize(2);
+    todo.push_back({0u, n, 0u});
+    while (!todo.empty()) {
+        const Job j = todo.back(); todo.pop_back();
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+        for (uint32_t i = j.lo; i < j.hi; ++i) {
+            const sqt_sphere &s = sp[out.order[i]];
+            const double rr = (double)s.radius * (1.0 + 1.0 / 524288.0);
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = std::fmin(lo[k], (double)s.center[k] - rr); hi[k] = std::fmax(hi[k], (double)s.center[k] + rr);
+                clo[k] = std::fmin(clo[k], (double)s.center[k]); chi[k] = std::fmax(chi[k], (double)s.center[k]);
+            }
+        }
+        auto dn_ = [](double x) { return std::nextafterf((float)x, -INFINITY); };
+        auto up_ = [](double x) { return std::nextafterf((float)x, INFINITY); };
+        uint32_t a, b;
+        if (j.hi - j.lo <= 4u) { a = j.lo; b = (j.hi - j.lo) | kLeaf; }
+        else {
+            int ax = 0;
+            if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+            if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+            const uint32_t mid = j.lo + (j.hi - j.lo) / 2;
+            std::nth_element(out.order.begin() + j.lo, out.order.begin() + mid, out.order.begin() + j.hi,
+                             [&](uint32_t x, uint32_t y) { return sp[x].center[ax] < sp[y].center[ax] || (sp[x].center[ax] == sp[y].center[ax] && x < y); });
+            a = (uint32_t)(out.nodes.size() / 2); b = a + 1;
+            out.nodes.resize(out.nodes.size() + 4);
+            todo.push_back({mid, j.hi, b});
+            todo.push_back({j.lo, mid, a});
+            a |= (uint32_t)ax << 30;
+        }
+        out.nodes[2 * (size_t)j.node] = mk4(dn_(lo[0]), dn_(lo[1]), dn_(lo[2]), up_(hi[0]));
+        out.nodes[2 * (size_t)j.node + 1] = mk4(up_(hi[1]), up_(hi[2]), u2f(a), u2f(b));
+    }
 }
 
 }  // namespace sqt

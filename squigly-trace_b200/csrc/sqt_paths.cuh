@@ -20,7 +20,13 @@
 
 namespace sqt {
 
-struct PathStats { unsigned long long rays, samples, primary_reused; };
+// per-lane tallies; 32 bits on the device (a lane traces a few thousand rays per launch; the warp sums them in 64 bits)
+#if defined(__CUDA_ARCH__)
+typedef unsigned int stat_t;
+#else
+typedef unsigned long long stat_t;
+#endif
+struct PathStats { stat_t rays, samples, primary_reused; };
 
 // pixel owned by this rank for work item w (pixel-group partition: groups of 32 consecutive pixels,
 // round-robin over ranks).  Returns -1 for the padding of the last group.
@@ -332,7 +338,7 @@ struct PrimaryPolicy {
             else {                                        // every sample of this pixel is black (Lib.hs:130): nothing to trace
                 int k0, k1;
                 sample_range(p, k0, k1);
-                if (k1 > k0) { st.samples += (unsigned long long)(k1 - k0); st.primary_reused += (unsigned long long)(k1 - k0); }
+                if (k1 > k0) { st.samples += (stat_t)(k1 - k0); st.primary_reused += (stat_t)(k1 - k0); }
             }
             w += stride;
         }
@@ -372,7 +378,7 @@ struct CastPolicy {
         sample_range(p, k0, k1);
         float sr = 0.0f, sg = 0.0f, sb = 0.0f;
         for (int k = k0; k < k1; ++k) { sr = XADD(sr, cr); sg = XADD(sg, cg); sb = XADD(sb, cb); }
-        st.samples += (unsigned long long)(k1 > k0 ? k1 - k0 : 0);
+        st.samples += (stat_t)(k1 > k0 ? k1 - k0 : 0);
         accum[3 * pixel] = sr; accum[3 * pixel + 1] = sg; accum[3 * pixel + 2] = sb;
         w += stride;
         stage = 0;
@@ -429,6 +435,7 @@ SQT_HD_NOINLINE void run_lane(const SceneView &sc, Policy &pol, Counters *cn) {
         if (L.state == ST_DESC) desc_step<COUNT>(sc, L, ra, cn);
         if (L.state == ST_ENTER) enter_step<COUNT>(sc, L, ra, cn);
         if (L.state == ST_LEAF) tri_step<COUNT>(sc, L, cn);
+        if (L.state == ST_SPH) sphere_step(sc, L, ra);
     }
 }
 

@@ -16,6 +16,8 @@ using namespace sqt;
 struct emu_scene {
     DeviceLayout lay;
     std::vector<float4> tris, spheres, leaves;
+    SphereBvh bvh;
+    int sphere_bvh = 1;
     SceneView view;
     std::string err;
 };
@@ -65,7 +67,13 @@ void emu_set_spheres(emu_scene *s, const sqt_sphere *sp, unsigned n) {
         s->spheres[2 * k + 1] = float4{u2f(sp[k].material), 0, 0, 0};
     }
     s->view.spheres = s->spheres.data(); s->view.n_spheres = n;
+    s->view.sph_nodes = nullptr; s->view.sph_order = nullptr;
+    if (n && s->sphere_bvh) {
+        build_sphere_bvh(sp, n, s->bvh);
+        s->view.sph_nodes = s->bvh.nodes.data(); s->view.sph_order = s->bvh.order.data();
+    }
 }
+void emu_set_sphere_bvh(emu_scene *s, int on) { s->sphere_bvh = on; if (!on) { s->view.sph_nodes = nullptr; s->view.sph_order = nullptr; } }
 void emu_set_sbuf_budget(long long bytes) { sbuf_budget = bytes; }
 
 void emu_intersect_batch(emu_scene *s, const float *org, const float *dir, long long n, int *tri_out, float *dist_out,
@@ -117,6 +125,7 @@ int emu_intersect_batch_interleaved(emu_scene *s, const float *org, const float 
                     const TriData d = tri_load(s->view, l.child + (uint32_t)l.i);
                     tri_apply<false>(l, ra.ray(), d, &cn);
                 }
+                else if (l.state == ST_SPH) sphere_step(s->view, l, ra);
             }
         }
         for (int k = 0; k < m; ++k) {                        // report like BatchPolicy: position in the parsed list, -1 = Nothing
@@ -242,6 +251,7 @@ long long emu_trace_lane(emu_scene *s, const sqt_camera *cam, const sqt_render_p
             n++;
         } else if (L.state == ST_ENTER) { enter_step<false>(s->view, L, ra, &cn); if (n < cap) out[n] = 'E'; n++; }
         else if (L.state == ST_LEAF) { tri_step<false>(s->view, L, &cn); if (n < cap) out[n] = 'L'; n++; }
+        else if (L.state == ST_SPH) sphere_step(s->view, L, ra);
     }
     return n < cap ? n : cap;
 }
@@ -263,6 +273,7 @@ void emu_leaf_cull_stats(emu_scene *s, const float *org, const float *dir, long 
         while (L.state != ST_DONE) {
             if (L.state == ST_RET) ret_step(s->view, L, ra);
             if (L.state == ST_DESC) desc_step<false>(s->view, L, ra, &cn);
+            if (L.state == ST_SPH) sphere_step(s->view, L, ra);
             if (L.state == ST_ENTER) enter_step<false>(s->view, L, ra, &cn);
             if (L.state == ST_LEAF) {
                 const uint32_t first = L.child, count = (uint32_t)L.i + 1;
@@ -311,6 +322,7 @@ void emu_group_cull_stats(emu_scene *s, const float *org, const float *dir, long
         while (L.state != ST_DONE) {
             if (L.state == ST_RET) ret_step(s->view, L, ra);
             if (L.state == ST_DESC) desc_step<false>(s->view, L, ra, &cn);
+            if (L.state == ST_SPH) sphere_step(s->view, L, ra);
             if (L.state == ST_ENTER) enter_step<false>(s->view, L, ra, &cn);
             if (L.state == ST_LEAF) {
                 const uint32_t first = L.child, count = (uint32_t)L.i + 1;

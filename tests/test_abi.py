@@ -71,3 +71,37 @@ def test_product_does_not_reference_the_oracle():
     for lib in (pysqt.LIB_B200, pysqt.LIB_HOST):
         ldd = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout
         assert "oracle" not in ldd and "emu" not in ldd
+
+
+def test_struct_layout_matches_the_binding_documentation(tmp_path):
+    """The C structs of include/sqt.h (compiled with gcc, offsetof), the ctypes mirror used by every test, and the byte
+    offsets INTEGRATION.md gives the Haskell Storable instances must be the same numbers."""
+    import ctypes as C
+    import pysqt
+    src = tmp_path / "layout.c"
+    fields = {
+        "sqt_scene_desc": ["root_bounds", "nodes", "n_nodes", "tris", "n_tris", "mats", "n_mats"],
+        "sqt_camera": ["position", "rotation"],
+        "sqt_render_params": ["rows", "cols", "xdiv", "ydiv", "seed_stride", "spp", "max_depth", "mode", "seed", "flags", "reserved"],
+        "sqt_node": ["lmax", "rmin", "a", "b"],
+        "sqt_tri": ["v0", "e1", "e2", "material", "orig_index", "pad"],
+        "sqt_material": ["reflective", "surf_color", "emissive", "emit_color"],
+        "sqt_stats": ["device_ms", "primary_ms", "paths_ms", "tonemap_ms", "reduce_ms", "h2d_ms", "d2h_ms", "rays_traced"],
+    }
+    body = "".join('printf("%s %%zu", sizeof(%s));%s printf("\\n");\n' % (
+        s, s, "".join(' printf(" %%zu", offsetof(%s, %s));' % (s, f) for f in fs)) for s, fs in fields.items())
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sqt.h"\nint main(void){\n%s return 0; }\n' % body)
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(pysqt.ROOT, "include"), "-o", str(exe), str(src)])
+    got = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in subprocess.check_output([str(exe)], text=True).splitlines()}
+    mirror = {"sqt_scene_desc": pysqt.SceneDesc, "sqt_camera": pysqt.Camera, "sqt_render_params": pysqt.RenderParams, "sqt_node": pysqt.Node,
+              "sqt_tri": pysqt.Tri, "sqt_material": pysqt.Material, "sqt_stats": pysqt.Stats}
+    for s, fs in fields.items():
+        T = mirror[s]
+        assert got[s] == [C.sizeof(T)] + [getattr(T, f).offset for f in fs], s
+    # the numbers written into INTEGRATION.md section 2
+    assert got["sqt_scene_desc"] == [72, 0, 24, 32, 40, 48, 56, 64]
+    assert got["sqt_camera"] == [48, 0, 12]
+    assert got["sqt_render_params"] == [48, 0, 4, 8, 12, 16, 20, 24, 28, 32, 40, 44]
+    assert got["sqt_node"][0] == 16 and got["sqt_tri"] == [48, 0, 12, 24, 36, 40, 44] and got["sqt_material"][0] == 32
+    assert got["sqt_stats"][0] == 168

@@ -209,3 +209,51 @@ def test_non_finite_planes_disable_interval_stepping():
     e = Emu(hs)
     org, dirs = random_rays(8000, 29, lo=-2.5, hi=2.5)
     assert_same_hits(e.intersect_batch(org, dirs), osc.intersect_batch(org, dirs), "infinite planes")
+
+
+def many_spheres(n, seed, duplicates=True, log_r=(-2.5, -0.6)):
+    """n spheres inside the reference scene's bounds; every 16th one is an exact copy of an earlier one (same centre and
+    radius -> identical dist: the earlier index must win), radii log-uniform from tiny to large."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1.9, 1.9, (n, 3)).astype(np.float32)
+    r = (10.0 ** rng.uniform(log_r[0], log_r[1], n)).astype(np.float32)
+    m = rng.integers(0, 6, n)
+    if duplicates:
+        for k in range(16, n, 16):
+            j = int(rng.integers(0, k))
+            c[k] = c[j]; r[k] = r[j]
+    return [(float(c[k, 0]), float(c[k, 1]), float(c[k, 2]), float(r[k]), int(m[k])) for k in range(n)]
+
+
+def test_sphere_hierarchy_gives_the_definitions_result(host_scene, camera):
+    """The spheres are found through a bounding-volume hierarchy (sphere_step); the result must be the definition's --
+    closest of [BIH hit, sphere 0, sphere 1, ..], earliest on ties -- for camera rays, incoherent rays, rays from sphere
+    surfaces, duplicated spheres, and the adversarial rays (zero / tiny / huge components take the literal loop)."""
+    e = Emu(host_scene)
+    osc = O.Scene.load(pysqt.ROOT + "/data/scene.obj", pysqt.ROOT + "/data")
+    osc.make_bih()
+    sph = many_spheres(3000, 5)
+    e.set_spheres(sph); osc.set_spheres(sph)
+    org, dirs = O.make_rays(O.make_params(120, 90, 1), camera)
+    o2, d2 = random_rays(30000, 19)
+    v9, _ = osc.tris()
+    o3, d3 = adversarial_rays(v9, seed=4, n_each=64)
+    c = np.array([s[:3] for s in sph[:2000]], np.float32); rr = np.array([s[3] for s in sph[:2000]], np.float32)
+    rng = np.random.default_rng(2)
+    u = rng.normal(size=(2000, 3)).astype(np.float32); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    o4 = (c + u * rr[:, None]).astype(np.float32); d4 = rng.normal(size=(2000, 3)).astype(np.float32)      # origins ON sphere surfaces
+    org = np.concatenate([org, o2, o3, o4]); dirs = np.concatenate([dirs, d2, d3, d4])
+    want = osc.intersect_batch(org, dirs)
+    got = e.intersect_batch(org, dirs)
+    assert_same_hits(got, want, "sphere hierarchy")
+    assert (want[0] >= osc.n_tris).sum() > 8000
+    import ctypes as C
+    from common import emu_lib
+    emu_lib().emu_set_sphere_bvh.argtypes = [C.c_void_p, C.c_int]
+    emu_lib().emu_set_sphere_bvh(e.h, 0)                    # the literal loop over all spheres, same answer
+    assert_same_hits(e.intersect_batch(org[:6000], dirs[:6000]), (want[0][:6000], want[1][:6000], want[2][:6000]), "sphere loop")
+    emu_lib().emu_set_sphere_bvh(e.h, 1)
+    e.set_spheres(sph)
+    got = e.render(camera, pysqt.make_params(64, 48, 4, max_depth=6, seed=3))
+    ref = osc.render(camera, O.make_params(64, 48, 4, max_depth=6, seed=3, trig=1))
+    assert np.array_equal(bits(got["accum"]), bits(ref["accum"])) and np.array_equal(got["rgb8"], ref["rgb8"])
