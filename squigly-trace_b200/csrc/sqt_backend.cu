@@ -61,6 +61,7 @@ struct sqt_ctx {
     int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
     PoolTune pool_tune = {4, 10, 16};
     int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1
+    int pool_carveout = 0;              // shared-memory carve-out of k_paths_pool in percent of 228 KB (0 = the driver's choice)
     float4 *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0, cap_stack_entries = 0;
     bool comm_broken = false;           // the communicator was aborted after a rank failed
     // group
@@ -89,6 +90,7 @@ static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v
 static void read_env_tuning(sqt_ctx *c) {
     if (const char *t = getenv("SQT_POOL")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 4) c->pool_k = k == 3 ? 4 : (int)k; }      // rays per warp = 32 * K, K a power of two
     if (const char *t = getenv("SQT_POOL_BLOCKS")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 32) c->pool_blocks = (int)k; }
+    if (const char *t = getenv("SQT_POOL_CARVEOUT")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 100) c->pool_carveout = (int)k; }
     if (const char *t = getenv("SQT_POOL_TUNE")) {       // "burst_t,t_leave,c_min"
         int a, b, cm;
         if (sscanf(t, "%d,%d,%d", &a, &b, &cm) == 3) c->pool_tune = {clampi(a, 1, 64), clampi(b, 0, 31), clampi(cm, 1, 32)};
@@ -439,6 +441,7 @@ static int pool_step(sqt_ctx *ctx, const RenderParams &d, const RoundInfo &rd, i
         if (pct > 100) pct = 100;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
+    if (ctx->pool_carveout > 0) CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->pool_carveout));
     long long grid = (long long)ctx->sm_count * per_sm, want = (nitems + 128 * K - 1) / (128 * K);
     if (want < grid) grid = want ? want : 1;
     const long long slots = grid * 4 * 32 * K;
