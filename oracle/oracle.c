@@ -9,8 +9,12 @@
  * PARITY UNPINNED: the reference ships no tests, golden vectors or known-answer values
  * (test/Spec.hs:1-2) and cannot be compiled in this image (no ghc/stack/cabal).  This file is a
  * literal, function-by-function restatement of the Haskell sources, every function citing the
- * lines it follows.  The only checks available are the reference's own differential pair
- * (naiveIntersect vs intersectBIH) and a low-frequency comparison with render/example.png.
+ * lines it follows.  What checks it: the reference's own differential pair (naiveIntersect vs
+ * intersectBIH); a low-frequency comparison with render/example.png; and, since round 2, a second
+ * restatement written independently from the Haskell (tests/hs_literal.py: literal recursion and
+ * lists in Python float32) that must agree with this file bit for bit on the BIH, on 10 k rays
+ * incl. the adversarial set, and on the raytrace fold (tests/test_hs_literal.py).  The pin by the
+ * reference itself is prepared (tests/golden/ghc/Dump.hs + test_ghc_fixture) but needs GHC.
  *
  * Arithmetic: GHC 8.0.2 Float = IEEE binary32 on SSE scalar, no fusion.  Build with
  *   gcc -O2 -ffp-contract=off -fno-fast-math   (see oracle/Makefile)
