@@ -46,7 +46,7 @@ enum {
 /* ---- flattened BIH (BIH.hs:26,37-43), nodes in any order with node 0 = root ------------------
  * Branch (BIHN axis lmax rmin) l r : a = index(l) | axis<<30 ,  b = index(r)             (axis X=0,Y=1,Z=2)
  * Leaf tris                         : a = first triangle in tris[] , b = count | 0x80000000   (lmax,rmin ignored)
- * At most 2^28 - 1 nodes and 2^27 - 1 triangles.  Child boxes are NOT stored: the library derives them exactly as
+ * At most 2^27 - 1 nodes and 2^27 - 1 triangles.  Child boxes are NOT stored: the library derives them exactly as
  * BIH.hs:130-141 does, by clipping the parent's box (plain copies of lmax/rmin, no arithmetic).  The `pad` word of
  * a triangle is ignored on input (the device copy uses it). */
 typedef struct sqt_node {

@@ -30,6 +30,7 @@ struct sqt_ctx {
     // scene
     bool has_scene = false;
     SceneView sc = {};
+    float4 *d_slabs = nullptr, *d_tight = nullptr; uint32_t *d_levels = nullptr;          // subtree slabs (+ upload scratch)
     float4 *d_nodes = nullptr, *d_boxes = nullptr, *d_tris = nullptr, *d_mats = nullptr, *d_leaves = nullptr, *d_spheres = nullptr;
     float4 *d_sph_nodes = nullptr; uint32_t *d_sph_order = nullptr; int sphere_bvh = 1;      // extension: hierarchy over the spheres
     uint2 *d_ranges = nullptr;          // (first, count) per leaf, input of k_leaf_records
@@ -61,6 +62,7 @@ struct sqt_ctx {
     int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
     PoolTune pool_tune = {4, 10, 16};
     int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1
+    float slab_ratio = kSlabRatioMax;   // subtree slabs: test a slab when it is at most this fraction of the clipped box (SQT_SLAB_RATIO, 0 = never)
     int pool_carveout = 0;              // shared-memory carve-out of k_paths_pool in percent of 228 KB (0 = the driver's choice)
     float4 *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0, cap_stack_entries = 0;
     bool comm_broken = false;           // the communicator was aborted after a rank failed
@@ -90,6 +92,7 @@ static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v
 static void read_env_tuning(sqt_ctx *c) {
     if (const char *t = getenv("SQT_POOL")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 4) c->pool_k = k == 3 ? 4 : (int)k; }      // rays per warp = 32 * K, K a power of two
     if (const char *t = getenv("SQT_POOL_BLOCKS")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 32) c->pool_blocks = (int)k; }
+    if (const char *t = getenv("SQT_SLAB_RATIO")) { char *e = nullptr; double v = strtod(t, &e); if (e != t && v >= 0.0 && v <= 2.0) c->slab_ratio = (float)v; }
     if (const char *t = getenv("SQT_POOL_CARVEOUT")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 100) c->pool_carveout = (int)k; }
     if (const char *t = getenv("SQT_POOL_TUNE")) {       // "burst_t,t_leave,c_min"
         int a, b, cm;
@@ -138,6 +141,7 @@ extern "C" int sqt_create(int device, sqt_ctx **out) {
 }
 
 static void free_scene(sqt_ctx *c) {
+    cudaFree(c->d_slabs); cudaFree(c->d_tight); cudaFree(c->d_levels); c->d_slabs = c->d_tight = nullptr; c->d_levels = nullptr;
     cudaFree(c->d_nodes); cudaFree(c->d_boxes); cudaFree(c->d_tris); cudaFree(c->d_mats); cudaFree(c->d_leaves); cudaFree(c->d_spheres); cudaFree(c->d_sph_nodes); cudaFree(c->d_sph_order); cudaFree(c->d_ranges);
     c->d_nodes = c->d_boxes = c->d_tris = c->d_mats = c->d_leaves = c->d_spheres = c->d_sph_nodes = nullptr; c->d_sph_order = nullptr; c->d_ranges = nullptr; c->has_scene = false;
     c->cap_branches = c->cap_leaves = c->cap_tris = c->cap_mats = 0;
@@ -178,8 +182,11 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 
 static int ensure_scene_capacity(sqt_ctx *ctx, size_t n_br, size_t n_lf, size_t n_tris, size_t n_mats) {
     if (n_br > ctx->cap_branches) {
-        cudaFree(ctx->d_nodes); cudaFree(ctx->d_boxes); ctx->d_nodes = ctx->d_boxes = nullptr; ctx->cap_branches = 0;
+        cudaFree(ctx->d_nodes); cudaFree(ctx->d_boxes); cudaFree(ctx->d_slabs); cudaFree(ctx->d_tight); cudaFree(ctx->d_levels);
+        ctx->d_nodes = ctx->d_boxes = ctx->d_slabs = ctx->d_tight = nullptr; ctx->d_levels = nullptr; ctx->cap_branches = 0;
         CU(cudaMalloc(&ctx->d_nodes, n_br * sizeof(float4))); CU(cudaMalloc(&ctx->d_boxes, 2 * n_br * sizeof(float4)));
+        CU(cudaMalloc(&ctx->d_slabs, n_br * sizeof(float4))); CU(cudaMalloc(&ctx->d_tight, 2 * n_br * sizeof(float4)));
+        CU(cudaMalloc(&ctx->d_levels, n_br * sizeof(uint32_t)));
         ctx->cap_branches = n_br;
     }
     if (n_lf > ctx->cap_leaves) {
@@ -242,7 +249,7 @@ static int upload_scene_to(sqt_ctx **ctxs, int n, const sqt_scene_desc *s) {
     const double t0 = now_ms();
     if (!s->nodes || s->n_nodes == 0) return fail(ctx, SQT_E_INVALID, "scene has no BIH nodes");
     if (s->n_tris && !s->tris) return fail(ctx, SQT_E_INVALID, "tris is NULL");
-    if (s->n_tris >= (1u << 27) || s->n_nodes >= (1u << 28)) return fail(ctx, SQT_E_UNSUPPORTED, "scene too large for the 27/28-bit indices");
+    if (s->n_tris >= (1u << 27) || s->n_nodes >= (1u << 27)) return fail(ctx, SQT_E_UNSUPPORTED, "scene too large for the 27-bit indices");
     uint32_t n_br = 0, n_lf = 0;
     for (uint32_t i = 0; i < s->n_nodes; ++i) { if (s->nodes[i].b & SQT_NODE_LEAF) ++n_lf; else ++n_br; }
     for (int g = 0; g < n; ++g) {
@@ -265,6 +272,14 @@ static int upload_scene_to(sqt_ctx **ctxs, int n, const sqt_scene_desc *s) {
     if (tri_status.load()) return fail(ctx, tri_status.load(), "%s", tri_err.c_str());
     std::vector<uint2> ranges(lay.leaf_first.size());
     for (size_t k = 0; k < ranges.size(); ++k) ranges[k] = make_uint2(lay.leaf_first[k], lay.leaf_count[k]);
+    // branches sorted by depth (counting sort): the bottom-up pass of the subtree slabs runs one launch per level
+    std::vector<uint32_t> level_off(lay.height + 2, 0u), level_nodes(lay.n_branches ? lay.n_branches : 1);
+    for (uint32_t b = 0; b < lay.n_branches; ++b) level_off[lay.branch_depth[b] + 1]++;
+    for (size_t d = 1; d < level_off.size(); ++d) level_off[d] += level_off[d - 1];
+    {
+        std::vector<uint32_t> fill(level_off.begin(), level_off.end() - 1);
+        for (uint32_t b = 0; b < lay.n_branches; ++b) level_nodes[fill[lay.branch_depth[b]]++] = b;
+    }
     const uint32_t n_leaves = n_lf;
     for (int g = 0; g < n; ++g) {
         sqt_ctx *c = ctxs[g];
@@ -285,6 +300,17 @@ static int upload_scene_to(sqt_ctx **ctxs, int n, const sqt_scene_desc *s) {
             k_check_materials<<<(s->n_tris + 255) / 256, 256, 0, st>>>(c->d_tris, s->n_tris, s->n_mats, c->d_flag);
             CU(cudaGetLastError());
         }
+        if (lay.n_branches) {
+            CU(cudaMemcpyAsync(c->d_levels, level_nodes.data(), (size_t)lay.n_branches * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            for (uint32_t d = lay.height; d >= 1; --d) {                      // deepest level first
+                const uint32_t lo = level_off[d], cnt = level_off[d + 1] - lo;
+                if (!cnt) continue;
+                k_branch_tight<<<(cnt + 255) / 256, 256, 0, st>>>(c->d_levels + lo, cnt, c->d_nodes, c->d_leaves, c->d_tight);
+                CU(cudaGetLastError());
+            }
+            k_child_slabs<<<(lay.n_branches + 255) / 256, 256, 0, st>>>(c->d_nodes, lay.n_branches, c->d_boxes, c->d_tight, lay.s_max, lay.c_max, c->slab_ratio, c->d_slabs);
+            CU(cudaGetLastError());
+        }
     }
     for (int g = 0; g < n; ++g) {
         sqt_ctx *c = ctxs[g];
@@ -295,14 +321,16 @@ static int upload_scene_to(sqt_ctx **ctxs, int n, const sqt_scene_desc *s) {
         CU(cudaStreamSynchronize(c->stream));
         if (flag[0] != 0xffffffffu) return fail(ctxs[0], SQT_E_INVALID, "triangle %u: material %u out of range", flag[0], s->tris[flag[0]].material);
         SceneView v = {};
-        v.nodes = c->d_nodes; v.boxes = c->d_boxes; v.tris = c->d_tris; v.mats = c->d_mats; v.leaves = c->d_leaves;
+        v.nodes = c->d_nodes; v.boxes = c->d_boxes; v.tris = c->d_tris; v.mats = c->d_mats; v.leaves = c->d_leaves; v.slabs = c->d_slabs;
+        for (int k = 0; k < 3; ++k) v.tame_c[k] = lay.tame_c[k];
+        v.tame_r = lay.tame_r;
         v.leaf_cull = (uint32_t)c->leaf_cull;
         for (int k = 0; k < 3; ++k) { v.root_lo[k] = s->root_bounds[k]; v.root_hi[k] = s->root_bounds[3 + k]; }
         v.n_branches = lay.n_branches; v.n_tris = s->n_tris; v.n_mats = s->n_mats;
         v.root_is_leaf = (s->nodes[0].b & SQT_NODE_LEAF) ? 1u : 0u;
         v.planes_finite = (uint32_t)lay.planes_finite;
         c->sc = v; c->has_scene = true; c->terminate_on_black_ok = lay.terminate_on_black_ok; c->tree_height = lay.height;
-        c->upload_bytes = (uint64_t)s->n_tris * 48 + lay.nodes.size() * 16 + lay.boxes.size() * 16 + lay.mats.size() * 16 + ranges.size() * 8 + 8;
+        c->upload_bytes = (uint64_t)s->n_tris * 48 + lay.nodes.size() * 16 + lay.boxes.size() * 16 + lay.mats.size() * 16 + ranges.size() * 8 + (uint64_t)lay.n_branches * 4 + 8;
         c->upload_layout_ms = t1 - t0;
         c->upload_ms = now_ms() - t0;
     }

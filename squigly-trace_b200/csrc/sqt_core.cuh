@@ -55,8 +55,8 @@ namespace sqt {
 
 // ---------------------------------------------------------------------------- device records
 // Branch node, 16 B = ONE 128-bit load: exactly the reference's BIHN (BIH.hs:37) plus the two child references:
-//   (lmax, rmin, L, R)      L = kLeaf? | kSlow? | axis << 28 | index      R = kLeaf? | index
-// index = position in the branch array (child is a Branch) or in the leaf array (child is a Leaf), < 2^28.
+//   (lmax, rmin, L, R)      L = kLeaf? | kSlow? | axis << 28 | kTight? | index      R = kLeaf? | kTight? | index
+// index = position in the branch array (child is a Branch) or in the leaf array (child is a Leaf), < 2^27.
 // The traversal carries the ray's parametric interval (tmin, tmax) through the box of the subtree it is about to
 // enter -- the two numbers intersectsBB (Geometry.hs:166-177) computes for that box -- and updates it per visit from
 // the ONE plane in which a child box differs from its parent (BIH.hs:130-141): the classic BIH step.  That is exact
@@ -77,7 +77,8 @@ constexpr uint32_t kLeaf = 0x80000000u;
 constexpr uint32_t kPhaseB = 0x40000000u;
 constexpr uint32_t kSlow = 0x40000000u;
 constexpr uint32_t kAxisShift = 28;
-constexpr uint32_t kIdxMask = 0x0fffffffu;
+constexpr uint32_t kTight = 0x08000000u;       // child reference: that Branch has a tight slab worth testing (slabs[index], section "subtree slabs")
+constexpr uint32_t kIdxMask = 0x07ffffffu;
 constexpr uint32_t kLeafFirstMask = 0x07ffffffu;
 constexpr uint32_t kLeafCountShift = 27;
 constexpr uint32_t kLeafLong = 31u;
@@ -89,6 +90,7 @@ constexpr int kStackEntries = 48;              // at most one entry per tree lev
 struct SceneView {
     const float4 *nodes;     // 1 float4 per branch
     const float4 *boxes;     // 2 float4 per branch (slow path only)
+    const float4 *slabs;     // 1 float4 per branch: conservative tight slab of its subtree (lo', hi', -, axis), see desc_step
     const float4 *leaves;    // 2 float4 per leaf
     const float4 *tris;      // 3 float4 per triangle: (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z, mat, orig, leaf count if >= 31)
     const float4 *mats;      // 3 float4 per material: (refl, surf.rgb) (emissive, emit.rgb) (ec.rgb, flags)
@@ -101,6 +103,7 @@ struct SceneView {
     uint32_t root_is_leaf;   // tree = Leaf: no box test at all (BIH.hs:105)
     uint32_t leaf_cull;      // 1 = skip leaves whose enlarged tight box the ray provably misses (exact, see enter_leaf)
     uint32_t planes_finite;  // every plane and box coordinate of the tree is finite (else every ray takes the literal path)
+    float tame_c[3], tame_r; // rays with |o - tame_c|_1 <= tame_r and |d|_1 <= 2 may use the subtree slabs (their margins assume it)
 };
 
 struct Ray { float ox, oy, oz, dx, dy, dz; };
@@ -263,6 +266,47 @@ SQT_HD_NOINLINE inline void make_leaf_record(const float4 *tris, uint32_t first,
     b1.w = u2f((cnt ? first : 0u) | (c5 << kLeafCountShift));
 }
 
+// ------------------------------------------------------------------------------ subtree slabs
+// Tight box + longest edge of everything below a Branch, aggregated bottom-up from the leaf records (2 x float4 like a
+// leaf record: (lo.xyz, hi.x) (hi.yz, E, empty? as bits)), and from it the ONE-axis slab desc_step intersects the ray's
+// interval with.  Runs on the device at upload (k_branch_tight / k_child_slabs) and on the host in tests/emu.
+struct TightRec { float4 t0, t1; };
+SQT_HD TightRec tight_of_leaf(const float4 *leaves, uint32_t leaf) {
+    TightRec r; r.t0 = leaves[2 * (size_t)leaf]; r.t1 = leaves[2 * (size_t)leaf + 1];
+    r.t1.w = u2f((f2u(r.t1.w) >> kLeafCountShift) == 0u ? 1u : 0u);          // an empty leaf contributes nothing
+    return r;
+}
+SQT_HD TightRec tight_union(const TightRec &a, const TightRec &b) {
+    if (f2u(a.t1.w)) return b;
+    if (f2u(b.t1.w)) return a;
+    TightRec r;
+    r.t0.x = fminf(a.t0.x, b.t0.x); r.t0.y = fminf(a.t0.y, b.t0.y); r.t0.z = fminf(a.t0.z, b.t0.z);
+    r.t0.w = fmaxf(a.t0.w, b.t0.w); r.t1.x = fmaxf(a.t1.x, b.t1.x); r.t1.y = fmaxf(a.t1.y, b.t1.y);
+    r.t1.z = fmaxf(a.t1.z, b.t1.z); r.t1.w = u2f(0u);
+    return r;
+}
+// Margin: the leaf-culling bound (enter_step) with its per-ray quantities replaced by their maxima over tame rays --
+// |d|_1 (1 + |d|_1) <= 6, |origin - v0|_1 <= s_max = 3 x the root's 1-norm half extent, |coordinates| <= c_max:
+//   m = 0.03 * (s_max + E) * 6 * E^2 + 1e-4 + 2^-20 * (c_max + s_max), rounded up.
+// The axis is the one on which the enlarged tight extent is the smallest fraction of the Branch's clipped box (c0, c1: the
+// box intersectBIH' passes down, BIH.hs:130-141); the slab is worth a test (return true) if that fraction is below ratio_max.
+SQT_HD bool make_slab(const TightRec &t, const float4 &c0, const float4 &c1, float s_max, float c_max, float ratio_max, float4 &slab) {
+    const float E = t.t1.z;
+    const float m = 1.001f * (0.03f * (s_max + E) * 6.0f * (E * E) + (1.0e-4f + 9.5367431640625e-7f * (c_max + s_max)));
+    const float tlo[3] = {t.t0.x, t.t0.y, t.t0.z}, thi[3] = {t.t0.w, t.t1.x, t.t1.y};
+    const float clo[3] = {c0.x, c0.y, c0.z}, chi[3] = {c0.w, c1.x, c1.y};
+    float best = 2.0f;
+    int bax = 0;
+    for (int k = 0; k < 3; ++k) {
+        const float len = chi[k] - clo[k];
+        const float a = fmaxf(tlo[k] - m, clo[k]), b = fminf(thi[k] + m, chi[k]);
+        const float ratio = (len > 0.0f && len < 1.0e30f && m == m && m < 1.0e30f) ? (b - a) / len : 2.0f;
+        if (ratio < best) { best = ratio; bax = k; }
+    }
+    slab.x = tlo[bax] - m; slab.y = thi[bax] + m; slab.z = best; slab.w = u2f((uint32_t)bax);
+    return f2u(t.t1.w) == 0u && best < ratio_max;
+}
+
 // ------------------------------------------------------------------------------ traversal
 // intersectBIH (BIH.hs:101-141) as an explicit-stack state machine that visits exactly the
 // subtrees the recursion visits, in the same order, and combines results with the same rules:
@@ -293,6 +337,7 @@ struct TravLane {
     int state;
     uint32_t sgn;               // bit k set iff dir[k] > 0 (leftToRight on axis k, BIH.hs:127)
     bool safe;                  // no slab value of this ray can be NaN -> interval stepping + FMNMX
+    bool tame;                  // safe, and origin / direction within the range the subtree-slab margins were derived for
     float4 *stack;              // entry e lives at stack[e * STRIDE] (STRIDE template parameter of the steps)
 };
 
@@ -456,6 +501,8 @@ SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
     L.safe = sc.planes_finite && finite_f(L.dfx) && finite_f(L.dfy) && finite_f(L.dfz) && finite_f(L.r.dx) && finite_f(L.r.dy) &&
              finite_f(L.r.dz) && finite_f(L.r.ox) && finite_f(L.r.oy) && finite_f(L.r.oz);
     L.sgn = (L.r.dx > 0.0f ? 1u : 0u) | (L.r.dy > 0.0f ? 2u : 0u) | (L.r.dz > 0.0f ? 4u : 0u);
+    L.tame = L.safe && (fabsf(L.r.dx) + fabsf(L.r.dy) + fabsf(L.r.dz)) <= 2.0f &&
+             (fabsf(L.r.ox - sc.tame_c[0]) + fabsf(L.r.oy - sc.tame_c[1]) + fabsf(L.r.oz - sc.tame_c[2])) <= sc.tame_r;
     L.tmin = 0.0f; L.tmax = 0.0f;
     if (sc.root_is_leaf) {                       // tree = Leaf: no box test at all (BIH.hs:105)
         L.child = 0u; L.i = (int)sc.n_tris - 1;
@@ -545,7 +592,25 @@ SQT_COLD float4 desc_children_literal(const float4 *boxes, uint32_t node, float 
 // 2 multiplications, 2 min/max and 3 compares instead of 12 + 12 + 20 + 4.
 template <bool COUNT, int STRIDE = 1, class RA>
 SQT_HD void desc_step(const SceneView &sc, TravLane &L, const RA &ra, Counters *cn) {
-    const float4 q = SQT_LDG4(sc.nodes + (size_t)L.child);
+    const uint32_t node = L.child & kIdxMask;
+    if ((L.child & kTight) && L.tame && sc.leaf_cull) {
+        // Subtree slab (not in the reference; exact like the leaf culling): every triangle below this
+        // Branch lies inside its tight box, and an accepted hit lies within the a-priori margin of its triangle.  One axis of
+        // that box, enlarged by the margin, is intersected with the interval the ray carries: the interval only shrinks, so a
+        // child test below can only change from "hit" to "miss" -- and only where no triangle could have been accepted.
+        const float4 sl = SQT_LDG4(sc.slabs + (size_t)node);
+        const int sax = (int)(f2u(sl.w) & 3u);
+        const float o = ra.o(sax), df = ra.df(sax);
+        const float t1 = (sl.x - o) * df, t2 = (sl.y - o) * df;
+        L.tmin = SQT_FMAX(L.tmin, SQT_FMIN(t1, t2));
+        L.tmax = SQT_FMIN(L.tmax, SQT_FMAX(t1, t2));
+        if (!(L.tmax > 0.0f && L.tmin < L.tmax)) {
+            if (COUNT) cn->leaves_culled += 1;
+            L.cur.tri = -1; L.state = ST_RET;
+            return;
+        }
+    }
+    const float4 q = SQT_LDG4(sc.nodes + (size_t)node);
     const uint32_t lb = f2u(q.z), rb = f2u(q.w);
     const int ax = (int)((lb >> kAxisShift) & 3u);
     const bool ltr = ((L.sgn >> ax) & 1u) != 0u;                            // BIH.hs:127
@@ -563,14 +628,14 @@ SQT_HD void desc_step(const SceneView &sc, TravLane &L, const RA &ra, Counters *
         const Ray r = ra.ray();
         float dfx, dfy, dfz;
         ra.dfv(dfx, dfy, dfz);
-        const float4 iv = desc_children_literal(sc.boxes, L.child, q.x, q.y, ax, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, dfx, dfy, dfz, L.safe);
+        const float4 iv = desc_children_literal(sc.boxes, node, q.x, q.y, ax, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, dfx, dfy, dfz, L.safe);
         const bool hit_l = iv.y > 0.0f && iv.x < iv.y, hit_r = iv.w > 0.0f && iv.z < iv.w;      // Geometry.hs:177
         hit_n = ltr ? hit_l : hit_r; hit_f = ltr ? hit_r : hit_l;
         n_min = ltr ? iv.x : iv.z; n_max = ltr ? iv.y : iv.w;
         f_min = ltr ? iv.z : iv.x; f_max = ltr ? iv.w : iv.y;
     }
     if (!(hit_n || hit_f)) { L.cur.tri = -1; L.state = ST_RET; return; }
-    const uint32_t nref = (ltr ? lb : rb) & (kLeaf | kIdxMask), fref = (ltr ? rb : lb) & (kLeaf | kIdxMask);
+    const uint32_t nref = (ltr ? lb : rb) & (kLeaf | kTight | kIdxMask), fref = (ltr ? rb : lb) & (kLeaf | kTight | kIdxMask);
     if (hit_n && hit_f) {                       // phase A entry: the far child, its interval, the plane isClose compares with
         float4 e;
         e.x = u2f(fref | ((uint32_t)ax << kAxisShift)); e.y = f_min; e.z = f_max; e.w = ltr ? q.y : q.x;      // rmin : lmax
@@ -580,7 +645,7 @@ SQT_HD void desc_step(const SceneView &sc, TravLane &L, const RA &ra, Counters *
     const uint32_t ref = hit_n ? nref : fref;
     L.tmin = hit_n ? n_min : f_min;
     L.tmax = hit_n ? n_max : f_max;
-    L.child = ref & kIdxMask;
+    L.child = ref & (kTight | kIdxMask);
     L.state = (ref & kLeaf) ? ST_ENTER : ST_DESC;
 }
 
@@ -641,7 +706,7 @@ SQT_HD void ret_step(const SceneView &sc, TravLane &L, const RA &ra) {
             slot = b;
         } else L.sp -= 1;
         L.tmin = e.y; L.tmax = e.z;
-        L.child = w & kIdxMask;
+        L.child = w & (kTight | kIdxMask);
         L.state = (w & kLeaf) ? ST_ENTER : ST_DESC;
         return;
     }

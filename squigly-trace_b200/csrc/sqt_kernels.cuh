@@ -8,7 +8,8 @@
 //   k_accumulate       : adds a round's samples to the per-pixel sums in sample order (Lib.hs:88)
 //   k_raycast          : --cast mode (Lib.hs:141-151)
 //   k_tonemap          : mean + rgbFloatToPixelRGB (Lib.hs:88-104)
-//   k_leaf_records, k_check_materials : scene upload (leaf records from the triangles; material index validation)
+//   k_leaf_records, k_check_materials, k_branch_tight, k_child_slabs : scene upload (leaf records from the triangles; material
+//                        index validation; tight subtree slabs bottom-up)
 //   k_fp32_peak, k_l2_read : roofline denominators measured on the device
 #pragma once
 #include <cuda_runtime.h>
@@ -283,7 +284,7 @@ struct PoolTune { int burst_t, t_leave, c_min; };
 
 // 16 words = 64 B per ray in shared memory; the first nine are what PoolRay reads.  PF_TMIN holds the interval's lower
 // end while the ray descends and `i` (triangles left - 1) for a ray that starts inside a leaf (root leaf);
-// PF_FLAGS = state | safe << 8 | sgn << 16 | sp << 24.
+// PF_FLAGS = state | safe << 8 | tame << 9 | sgn << 16 | sp << 24.
 enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_TMIN, PF_TMAX, PF_CTRI, PF_CT, PF_CDIST,
        PF_FLAGS, PF_WORDS };
 enum { KT = 0, KL = 1, KR = 2, KS = 3, KNONE = 4 };
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             if (act) {
                 L.child = PW(PF_CHILD, slot); L.tmin = u2f(PW(PF_TMIN, slot)); L.tmax = u2f(PW(PF_TMAX, slot));
                 fl = PW(PF_FLAGS, slot);
-                L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
+                L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.tame = ((fl >> 9) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
             }
             for (int b = 0; b < tn.burst_t; ++b) {
                 if (COUNT) { dbg_desc[b < 7 ? b : 7] += __popc(__ballot_sync(FULL, L.state == ST_DESC)); }
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 PW(PF_DFX, slot) = f2u(L.dfx); PW(PF_DFY, slot) = f2u(L.dfy); PW(PF_DFZ, slot) = f2u(L.dfz);
                 PW(PF_CHILD, slot) = L.child; PW(PF_TMIN, slot) = L.state == ST_LEAF ? (uint32_t)L.i : f2u(L.tmin); PW(PF_TMAX, slot) = f2u(L.tmax);
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
-                PW(PF_FLAGS, slot) = (uint32_t)L.state | (L.safe ? 0x100u : 0u) | (L.sgn << 16) | ((uint32_t)L.sp << 24);
+                PW(PF_FLAGS, slot) = (uint32_t)L.state | (L.safe ? 0x100u : 0u) | (L.tame ? 0x200u : 0u) | (L.sgn << 16) | ((uint32_t)L.sp << 24);
                 gp[0] = make_uint4(q.sidx, (uint32_t)q.j, (uint32_t)q.stream, (uint32_t)(q.stream >> 32));
                 gp[1] = make_uint4(f2u(q.saved_r), (uint32_t)(q.saved_j + 1) | (q.any_emit ? 0x10000u : 0u) | (q.in_flight ? 0x20000u : 0u), 0u, 0u);
             }
@@ -614,6 +615,43 @@ __global__ void __launch_bounds__(256) k_leaf_records(float4 *tris, const uint2 
 __global__ void __launch_bounds__(256) k_check_materials(const float4 *__restrict__ tris, uint32_t n_tris, uint32_t n_mats, uint32_t *bad) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_tris && __float_as_uint(tris[3 * (size_t)i + 2].y) >= n_mats) atomicMin(bad, i);
+}
+
+// scene upload, subtree slabs (sqt_core.cuh "subtree slabs"): tight records bottom-up, one launch per tree level (the
+// branches of a level only read records of deeper levels and of leaves), then every branch flags its branch children
+__global__ void __launch_bounds__(256) k_branch_tight(const uint32_t *__restrict__ level_nodes, uint32_t n, const float4 *__restrict__ nodes,
+                                                      const float4 *__restrict__ leaves, float4 *tight) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = level_nodes[i];
+    const float4 q = nodes[b];
+    const uint32_t w[2] = {__float_as_uint(q.z), __float_as_uint(q.w)};
+    TightRec c[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (w[k] & kLeaf) c[k] = tight_of_leaf(leaves, w[k] & kIdxMask);
+        else { c[k].t0 = tight[2 * (size_t)(w[k] & kIdxMask)]; c[k].t1 = tight[2 * (size_t)(w[k] & kIdxMask) + 1]; }
+    }
+    const TightRec r = tight_union(c[0], c[1]);
+    tight[2 * (size_t)b] = r.t0; tight[2 * (size_t)b + 1] = r.t1;
+}
+__global__ void __launch_bounds__(256) k_child_slabs(float4 *nodes, uint32_t n_branches, const float4 *__restrict__ boxes, const float4 *__restrict__ tight,
+                                                     float s_max, float c_max, float ratio_max, float4 *__restrict__ slabs) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_branches) return;
+    float4 q = nodes[b];
+    uint32_t w[2] = {__float_as_uint(q.z), __float_as_uint(q.w)};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (w[k] & kLeaf) continue;
+        const uint32_t c = w[k] & kIdxMask;
+        TightRec t; t.t0 = tight[2 * (size_t)c]; t.t1 = tight[2 * (size_t)c + 1];
+        float4 sl;
+        if (make_slab(t, boxes[2 * (size_t)c], boxes[2 * (size_t)c + 1], s_max, c_max, ratio_max, sl)) w[k] |= kTight;
+        slabs[c] = sl;
+    }
+    q.z = __uint_as_float(w[0]); q.w = __uint_as_float(w[1]);
+    nodes[b] = q;
 }
 
 // Non-fused FP32 issue rate: 16 independent chains per lane, alternating FMUL / FADD (the op mix of the

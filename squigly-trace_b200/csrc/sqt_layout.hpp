@@ -25,6 +25,10 @@ struct DeviceLayout {
     std::vector<float4> mats;       // 3 per material
     std::vector<uint32_t> leaf_first, leaf_count;   // triangle range per leaf (leaf order = order of first appearance in the node
                                                     // array); the leaf RECORDS are derived from the triangles by make_leaf_record
+    std::vector<uint32_t> branch_order;             // branches in the order of the walk (parents before children)
+    std::vector<uint32_t> branch_depth;             // depth of every branch (root = 1)
+    float s_max = 0.0f, c_max = 0.0f;               // constants of the subtree-slab margin (make_slab), tame_c / tame_r of SceneView
+    float tame_c[3] = {0, 0, 0}, tame_r = 0.0f;
     uint32_t n_branches = 0, n_slow = 0, height = 0;
     int planes_finite = 1;
     int terminate_on_black_ok = 0;
@@ -44,7 +48,7 @@ inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, st
     if (s->n_tris && !s->tris) return layout_fail(err, SQT_E_INVALID, "tris is NULL");
     if (!s->mats || s->n_mats == 0) return layout_fail(err, SQT_E_INVALID, "scene has no materials");
     if (s->n_mats > 65535) return layout_fail(err, SQT_E_UNSUPPORTED, "more than 65535 materials");
-    if (s->n_tris >= (1u << 27) || s->n_nodes >= (1u << 28)) return layout_fail(err, SQT_E_UNSUPPORTED, "scene too large for the 27/28-bit indices");
+    if (s->n_tris >= (1u << 27) || s->n_nodes >= (1u << 27)) return layout_fail(err, SQT_E_UNSUPPORTED, "scene too large for the 27-bit indices");
     const uint32_t N = s->n_nodes;
     std::vector<int32_t> branch_id(N, -1), leaf_id(N, -1);
     uint32_t n_br = 0, n_lf = 0;
@@ -55,6 +59,8 @@ inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, st
     out.leaf_first.assign(n_lf ? n_lf : 1, 0u); out.leaf_count.assign(n_lf ? n_lf : 1, 0u);
     struct Box { float lo[3], hi[3]; };
     std::vector<float4> dn((size_t)(n_br ? n_br : 1)), db((size_t)2 * (n_br ? n_br : 1));
+    out.branch_order.clear(); out.branch_order.reserve(n_br);
+    out.branch_depth.assign(n_br ? n_br : 1, 0u);
     std::vector<uint8_t> seen(N, 0);
     struct Item { uint32_t node; Box box; uint32_t depth; };
     std::vector<Item> todo;
@@ -102,6 +108,7 @@ inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, st
         if (!nested) { lref |= kSlow; ++n_slow; }
         lref |= ax << kAxisShift;
         const size_t b = (size_t)branch_id[it.node];
+        out.branch_order.push_back((uint32_t)b); out.branch_depth[b] = it.depth;
         dn[b] = mk4(nd.lmax, nd.rmin, u2f(lref), u2f(rref));
         db[2 * b] = mk4(it.box.lo[0], it.box.lo[1], it.box.lo[2], it.box.hi[0]);
         db[2 * b + 1] = mk4(it.box.hi[1], it.box.hi[2], 0.0f, 0.0f);
@@ -141,9 +148,45 @@ inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, st
         if (s->nodes[0].a != 0 || (s->nodes[0].b & ~SQT_NODE_LEAF) != s->n_tris)
             return layout_fail(err, SQT_E_INVALID, "root leaf must cover tris[0..n_tris)");
     }
+    {   // subtree-slab constants: tame rays start within 2 x the root's 1-norm half extent of its centre
+        float h1 = 0.0f, cm = 0.0f;
+        for (int k = 0; k < 3; ++k) {
+            out.tame_c[k] = 0.5f * (root.lo[k] + root.hi[k]);
+            h1 += 0.5f * (root.hi[k] - root.lo[k]);
+            cm = std::fmax(cm, std::fmax(std::fabs(root.lo[k]), std::fabs(root.hi[k])));
+        }
+        const bool ok = planes_finite && h1 >= 0.0f && h1 < 1.0e15f;
+        out.tame_r = ok ? 2.0f * h1 : -1.0f;                 // -1: no ray is tame, the slabs are never used
+        out.s_max = 3.0f * h1 * 1.0001f; out.c_max = cm;
+    }
     out.nodes.swap(dn); out.boxes.swap(db); out.mats.swap(dm);
     out.n_branches = n_br; out.n_slow = n_slow; out.height = height; out.terminate_on_black_ok = tob; out.planes_finite = planes_finite;
     return SQT_OK;
+}
+
+constexpr float kSlabRatioMax = 0.7f;     // a slab is tested when it is at most this fraction of the clipped box on its axis
+// Host version of what k_branch_tight + k_child_slabs do on the device (tests/emu): tight records bottom-up, then every
+// Branch decides for each Branch child whether its slab is worth a test and flags the reference (kTight).
+inline void compute_slabs_host(DeviceLayout &lay, const std::vector<float4> &leaves, std::vector<float4> &slabs, float ratio_max = kSlabRatioMax) {
+    const size_t nb = lay.n_branches;
+    std::vector<TightRec> tight(nb ? nb : 1);
+    slabs.assign(nb ? nb : 1, mk4(0, 0, 2.0f, 0));
+    auto child = [&](uint32_t ref) { return (ref & kLeaf) ? tight_of_leaf(leaves.data(), ref & kIdxMask) : tight[ref & kIdxMask]; };
+    for (size_t i = lay.branch_order.size(); i-- > 0;) {
+        const uint32_t b = lay.branch_order[i];
+        tight[b] = tight_union(child(f2u(lay.nodes[b].z)), child(f2u(lay.nodes[b].w)));
+    }
+    for (size_t b = 0; b < nb; ++b) {
+        uint32_t w[2] = {f2u(lay.nodes[b].z), f2u(lay.nodes[b].w)};
+        for (int c = 0; c < 2; ++c) {
+            if (w[c] & kLeaf) continue;
+            const uint32_t k = w[c] & kIdxMask;
+            float4 sl;
+            if (make_slab(tight[k], lay.boxes[2 * (size_t)k], lay.boxes[2 * (size_t)k + 1], lay.s_max, lay.c_max, ratio_max, sl)) w[c] |= kTight;
+            slabs[k] = sl;
+        }
+        lay.nodes[b].z = u2f(w[0]); lay.nodes[b].w = u2f(w[1]);
+    }
 }
 
 // ---- extension: bounding-volume hierarchy over the analytic spheres (sphere_step in sqt_core.cuh) -----------------

@@ -15,7 +15,7 @@ using namespace sqt;
 
 struct emu_scene {
     DeviceLayout lay;
-    std::vector<float4> tris, spheres, leaves;
+    std::vector<float4> tris, spheres, leaves, slabs;
     SphereBvh bvh;
     int sphere_bvh = 1;
     SceneView view;
@@ -47,6 +47,10 @@ emu_scene *emu_upload(const sqt_scene_desc *d) {
         make_leaf_record(s->tris.data(), s->lay.leaf_first[k], s->lay.leaf_count[k], s->leaves[2 * k], s->leaves[2 * k + 1]);
         if (s->lay.leaf_count[k] >= kLeafLong) s->tris[3 * (size_t)s->lay.leaf_first[k] + 2].w = u2f(s->lay.leaf_count[k]);
     }
+    compute_slabs_host(s->lay, s->leaves, s->slabs);
+    v.slabs = s->slabs.data();
+    for (int k = 0; k < 3; ++k) v.tame_c[k] = s->lay.tame_c[k];
+    v.tame_r = s->lay.tame_r;
     v.nodes = s->lay.nodes.data(); v.boxes = s->lay.boxes.data(); v.tris = s->tris.data(); v.mats = s->lay.mats.data(); v.leaves = s->leaves.data();
     v.leaf_cull = 1; v.planes_finite = (uint32_t)s->lay.planes_finite;
     for (int k = 0; k < 3; ++k) { v.root_lo[k] = d->root_bounds[k]; v.root_hi[k] = d->root_bounds[3 + k]; }
@@ -59,6 +63,11 @@ const char *emu_error(emu_scene *s) { return s->err.c_str(); }
 void emu_free(emu_scene *s) { delete s; }
 int emu_height(emu_scene *s) { return (int)s->lay.height; }
 int emu_slow_nodes(emu_scene *s) { return (int)s->lay.n_slow; }
+int emu_tight_children(emu_scene *s) {
+    int n = 0;
+    for (size_t b = 0; b < s->lay.n_branches; ++b) n += ((f2u(s->lay.nodes[b].z) & kTight) ? 1 : 0) + ((f2u(s->lay.nodes[b].w) & kTight) ? 1 : 0);
+    return n;
+}
 void emu_set_leaf_cull(emu_scene *s, int on) { s->view.leaf_cull = on ? 1u : 0u; }
 void emu_set_spheres(emu_scene *s, const sqt_sphere *sp, unsigned n) {
     s->spheres.assign((size_t)2 * (n ? n : 1), float4{0, 0, 0, 0});

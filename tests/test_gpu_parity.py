@@ -209,7 +209,7 @@ def test_synthetic_scenes_bit_exact(gpu_ctx, gen, n):
         got = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
     assert_same_hits(got, want, gen)
     assert got[3]["tri_tests"] == int(want[3][3]) and got[3]["branch_visits"] == int(want[3][0])
-    assert culled[3]["branch_visits"] == got[3]["branch_visits"] and culled[3]["tri_tests"] <= got[3]["tri_tests"]
+    assert culled[3]["branch_visits"] <= got[3]["branch_visits"] and culled[3]["tri_tests"] <= got[3]["tri_tests"]      # culling skips leaves and subtrees
 
 
 # ------------------------------------------------------------------ rendered image
