@@ -337,7 +337,7 @@ struct TravLane {
     int state;
     uint32_t sgn;               // bit k set iff dir[k] > 0 (leftToRight on axis k, BIH.hs:127)
     bool safe;                  // no slab value of this ray can be NaN -> interval stepping + FMNMX
-    bool tame;                  // safe, and origin / direction within the range the subtree-slab margins were derived for
+    bool tame;                  // culling is on, the ray is safe and within the range the subtree-slab margins were derived for
     float4 *stack;              // entry e lives at stack[e * STRIDE] (STRIDE template parameter of the steps)
 };
 
@@ -501,7 +501,7 @@ SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
     L.safe = sc.planes_finite && finite_f(L.dfx) && finite_f(L.dfy) && finite_f(L.dfz) && finite_f(L.r.dx) && finite_f(L.r.dy) &&
              finite_f(L.r.dz) && finite_f(L.r.ox) && finite_f(L.r.oy) && finite_f(L.r.oz);
     L.sgn = (L.r.dx > 0.0f ? 1u : 0u) | (L.r.dy > 0.0f ? 2u : 0u) | (L.r.dz > 0.0f ? 4u : 0u);
-    L.tame = L.safe && (fabsf(L.r.dx) + fabsf(L.r.dy) + fabsf(L.r.dz)) <= 2.0f &&
+    L.tame = L.safe && sc.leaf_cull && (fabsf(L.r.dx) + fabsf(L.r.dy) + fabsf(L.r.dz)) <= 2.0f &&
              (fabsf(L.r.ox - sc.tame_c[0]) + fabsf(L.r.oy - sc.tame_c[1]) + fabsf(L.r.oz - sc.tame_c[2])) <= sc.tame_r;
     L.tmin = 0.0f; L.tmax = 0.0f;
     if (sc.root_is_leaf) {                       // tree = Leaf: no box test at all (BIH.hs:105)
@@ -593,8 +593,9 @@ SQT_COLD float4 desc_children_literal(const float4 *boxes, uint32_t node, float 
 template <bool COUNT, int STRIDE = 1, class RA>
 SQT_HD void desc_step(const SceneView &sc, TravLane &L, const RA &ra, Counters *cn) {
     const uint32_t node = L.child & kIdxMask;
-    if ((L.child & kTight) && L.tame && sc.leaf_cull) {
-        // Subtree slab (not in the reference; exact like the leaf culling, DESIGN.md section 5): every triangle below this
+    const float4 q = SQT_LDG4(sc.nodes + (size_t)node);                    // issued before the slab test so that both loads overlap
+    if ((L.child & kTight) && L.tame) {
+        // Subtree slab (not in the reference; exact like the leaf culling, DESIGN.md section 5.1): every triangle below this
         // Branch lies inside its tight box, and an accepted hit lies within the a-priori margin of its triangle.  One axis of
         // that box, enlarged by the margin, is intersected with the interval the ray carries: the interval only shrinks, so a
         // child test below can only change from "hit" to "miss" -- and only where no triangle could have been accepted.
@@ -610,7 +611,6 @@ SQT_HD void desc_step(const SceneView &sc, TravLane &L, const RA &ra, Counters *
             return;
         }
     }
-    const float4 q = SQT_LDG4(sc.nodes + (size_t)node);
     const uint32_t lb = f2u(q.z), rb = f2u(q.w);
     const int ax = (int)((lb >> kAxisShift) & 3u);
     const bool ltr = ((L.sgn >> ax) & 1u) != 0u;                            // BIH.hs:127
