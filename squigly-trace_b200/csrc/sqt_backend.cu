@@ -62,7 +62,8 @@ struct sqt_ctx {
     int pool_k = 2;                     // 0: one ray per lane (k_paths) ; K > 0: ray pools of 32*K rays per warp (k_paths_pool)
     PoolTune pool_tune = {4, 10, 16};
     int pool_blocks = 0;                // cap on resident CTAs per SM for k_paths_pool (0 = occupancy limit); fewer CTAs leave more L1
-    float slab_ratio = kSlabRatioMax;   // subtree slabs: test a slab when it is at most this fraction of the clipped box (SQT_SLAB_RATIO, 0 = never)
+    float slab_ratio = kSlabRatioMax, slab_ratio_leaf = kSlabRatioMaxLeaf;   // subtree / leaf slabs: test a slab when it is at most this
+                                                                             // fraction of the clipped box (SQT_SLAB_RATIO=branch[,leaf], 0 = never)
     int pool_carveout = 0;              // shared-memory carve-out of k_paths_pool in percent of 228 KB (0 = the driver's choice)
     float4 *d_gstack = nullptr; uint16_t *d_gpm = nullptr; uint4 *d_gpath = nullptr; long long cap_pool_slots = 0, cap_stack_entries = 0;
     bool comm_broken = false;           // the communicator was aborted after a rank failed
@@ -92,7 +93,13 @@ static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v
 static void read_env_tuning(sqt_ctx *c) {
     if (const char *t = getenv("SQT_POOL")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 4) c->pool_k = k == 3 ? 4 : (int)k; }      // rays per warp = 32 * K, K a power of two
     if (const char *t = getenv("SQT_POOL_BLOCKS")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 32) c->pool_blocks = (int)k; }
-    if (const char *t = getenv("SQT_SLAB_RATIO")) { char *e = nullptr; double v = strtod(t, &e); if (e != t && v >= 0.0 && v <= 2.0) c->slab_ratio = (float)v; }
+    if (const char *t = getenv("SQT_SLAB_RATIO")) {
+        char *e = nullptr; double v = strtod(t, &e);
+        if (e != t && v >= 0.0 && v <= 2.0) {
+            c->slab_ratio = (float)v;
+            if (*e == ',') { const char *u = e + 1; double w = strtod(u, &e); if (e != u && w >= 0.0 && w <= 2.0) c->slab_ratio_leaf = (float)w; }
+        }
+    }
     if (const char *t = getenv("SQT_POOL_CARVEOUT")) { char *e = nullptr; long k = strtol(t, &e, 10); if (e != t && k >= 0 && k <= 100) c->pool_carveout = (int)k; }
     if (const char *t = getenv("SQT_POOL_TUNE")) {       // "burst_t,t_leave,c_min"
         int a, b, cm;
@@ -308,7 +315,8 @@ static int upload_scene_to(sqt_ctx **ctxs, int n, const sqt_scene_desc *s) {
                 k_branch_tight<<<(cnt + 255) / 256, 256, 0, st>>>(c->d_levels + lo, cnt, c->d_nodes, c->d_leaves, c->d_tight);
                 CU(cudaGetLastError());
             }
-            k_child_slabs<<<(lay.n_branches + 255) / 256, 256, 0, st>>>(c->d_nodes, lay.n_branches, c->d_boxes, c->d_tight, lay.s_max, lay.c_max, c->slab_ratio, c->d_slabs);
+            k_child_slabs<<<(lay.n_branches + 255) / 256, 256, 0, st>>>(c->d_nodes, lay.n_branches, c->d_boxes, c->d_tight, c->d_leaves, lay.s_max, lay.c_max, c->slab_ratio, c->slab_ratio_leaf, c->d_slabs);
+            k_flag_slabs<<<(lay.n_branches + 255) / 256, 256, 0, st>>>(c->d_nodes, lay.n_branches, c->d_slabs);
             CU(cudaGetLastError());
         }
     }

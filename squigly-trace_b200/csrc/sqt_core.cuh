@@ -57,6 +57,9 @@ namespace sqt {
 // Branch node, 16 B = ONE 128-bit load: exactly the reference's BIHN (BIH.hs:37) plus the two child references:
 //   (lmax, rmin, L, R)      L = kLeaf? | kSlow? | axis << 28 | kTight? | index      R = kLeaf? | kTight? | index
 // index = position in the branch array (child is a Branch) or in the leaf array (child is a Leaf), < 2^27.
+// Side array `slabs` (not in the reference, culling only -- "subtree slabs" below), 16 B per Branch: (lo, hi) of the left
+// child's conservative tight slab and (lo, hi) of the right child's; the two low mantissa bits of each lo hold the slab's
+// axis, or kSlabNone (not worth a test).  kTight in a reference to a Branch says that its record has a slab worth loading.
 // The traversal carries the ray's parametric interval (tmin, tmax) through the box of the subtree it is about to
 // enter -- the two numbers intersectsBB (Geometry.hs:166-177) computes for that box -- and updates it per visit from
 // the ONE plane in which a child box differs from its parent (BIH.hs:130-141): the classic BIH step.  That is exact
@@ -77,7 +80,8 @@ constexpr uint32_t kLeaf = 0x80000000u;
 constexpr uint32_t kPhaseB = 0x40000000u;
 constexpr uint32_t kSlow = 0x40000000u;
 constexpr uint32_t kAxisShift = 28;
-constexpr uint32_t kTight = 0x08000000u;       // child reference: that Branch has a tight slab worth testing (slabs[index], section "subtree slabs")
+constexpr uint32_t kTight = 0x08000000u;       // reference to a Branch: slabs[index] holds a child slab worth testing
+constexpr uint32_t kSlabNone = 3u;             // slab code (low mantissa bits of its lo): axis 0..2, or no slab worth a test
 constexpr uint32_t kIdxMask = 0x07ffffffu;
 constexpr uint32_t kLeafFirstMask = 0x07ffffffu;
 constexpr uint32_t kLeafCountShift = 27;
@@ -90,7 +94,7 @@ constexpr int kStackEntries = 48;              // at most one entry per tree lev
 struct SceneView {
     const float4 *nodes;     // 1 float4 per branch
     const float4 *boxes;     // 2 float4 per branch (slow path only)
-    const float4 *slabs;     // 1 float4 per branch: conservative tight slab of its subtree (lo', hi', -, axis), see desc_step
+    const float4 *slabs;     // 1 float4 per branch: tight slabs of its two children (culling only)
     const float4 *leaves;    // 2 float4 per leaf
     const float4 *tris;      // 3 float4 per triangle: (v0.xyz,e1.x) (e1.yz,e2.xy) (e2.z, mat, orig, leaf count if >= 31)
     const float4 *mats;      // 3 float4 per material: (refl, surf.rgb) (emissive, emit.rgb) (ec.rgb, flags)
@@ -307,6 +311,19 @@ SQT_HD bool make_slab(const TightRec &t, const float4 &c0, const float4 &c1, flo
     return f2u(t.t1.w) == 0u && best < ratio_max;
 }
 
+// lo bound of a slab with its code in the two low mantissa bits: moved outwards by 4..7 ulps, which keeps it conservative
+SQT_HD float pack_slab_lo(float lo, uint32_t code) {
+    if (!(fabsf(lo) >= 1.0e-30f)) lo = -1.0e-30f;                            // zero / denormal / NaN (NaN: the code is kSlabNone)
+    const uint32_t b = f2u(lo);
+    return u2f((((lo > 0.0f) ? b - 4u : b + 4u) & ~3u) | code);
+}
+// the box intersectBIH' passes to child `side` (0 = left, 1 = right) of a Branch with box (p0, p1), BIH.hs:130-141
+SQT_HD void clip_child_box(const float4 &p0, const float4 &p1, int ax, float lmax, float rmin, int side, float4 &c0, float4 &c1) {
+    c0 = p0; c1 = p1;
+    if (side == 0) { if (ax == 0) c0.w = lmax; else if (ax == 1) c1.x = lmax; else c1.y = lmax; }
+    else           { if (ax == 0) c0.x = rmin; else if (ax == 1) c0.y = rmin; else c0.z = rmin; }
+}
+
 // ------------------------------------------------------------------------------ traversal
 // intersectBIH (BIH.hs:101-141) as an explicit-stack state machine that visits exactly the
 // subtrees the recursion visits, in the same order, and combines results with the same rules:
@@ -326,6 +343,7 @@ SQT_HD bool make_slab(const TightRec &t, const float4 &c0, const float4 &c1, flo
 //   ST_SPH   (extension) the BIH part is finished, the analytic spheres are still to be folded in (sphere_step)
 enum : int { ST_DONE = 0, ST_DESC = 1, ST_LEAF = 2, ST_RET = 3, ST_EXIT = 4, ST_ENTER = 5, ST_SPH = 6 };
 
+constexpr uint32_t kRfUnsafe = 0x40000000u, kRfTame = 0x08000000u;
 struct TravLane {
     Ray r;
     float dfx, dfy, dfz;        // 1/dir (Geometry.hs:168), IEEE
@@ -335,9 +353,11 @@ struct TravLane {
     Hit cur;                    // result of the subtree that just returned / running best of the current leaf
     int sp;                     // stack entries in use
     int state;
-    uint32_t sgn;               // bit k set iff dir[k] > 0 (leftToRight on axis k, BIH.hs:127)
-    bool safe;                  // no slab value of this ray can be NaN -> interval stepping + FMNMX
-    bool tame;                  // culling is on, the ray is safe and within the range the subtree-slab margins were derived for
+    uint32_t rf;                // ray flags, placed so that one LOP3 combines them with a node / reference word:
+                                //   bit k (k = 0..2) set iff dir[k] > 0 (leftToRight on axis k, BIH.hs:127)
+                                //   kRfUnsafe (= kSlow): some slab value of this ray can be NaN -> literal six-slab path, no FMNMX
+                                //   kRfTame (= kTight): culling is on, the ray is safe and within the range the subtree-slab margins
+                                //   were derived for.  Other bits are ignored (the pool kernel keeps state and sp there).
     float4 *stack;              // entry e lives at stack[e * STRIDE] (STRIDE template parameter of the steps)
 };
 
@@ -498,11 +518,11 @@ SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
     L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
     L.sp = 0;
     L.dfx = XRCP(L.r.dx); L.dfy = XRCP(L.r.dy); L.dfz = XRCP(L.r.dz);
-    L.safe = sc.planes_finite && finite_f(L.dfx) && finite_f(L.dfy) && finite_f(L.dfz) && finite_f(L.r.dx) && finite_f(L.r.dy) &&
-             finite_f(L.r.dz) && finite_f(L.r.ox) && finite_f(L.r.oy) && finite_f(L.r.oz);
-    L.sgn = (L.r.dx > 0.0f ? 1u : 0u) | (L.r.dy > 0.0f ? 2u : 0u) | (L.r.dz > 0.0f ? 4u : 0u);
-    L.tame = L.safe && sc.leaf_cull && (fabsf(L.r.dx) + fabsf(L.r.dy) + fabsf(L.r.dz)) <= 2.0f &&
-             (fabsf(L.r.ox - sc.tame_c[0]) + fabsf(L.r.oy - sc.tame_c[1]) + fabsf(L.r.oz - sc.tame_c[2])) <= sc.tame_r;
+    const bool safe = sc.planes_finite && finite_f(L.dfx) && finite_f(L.dfy) && finite_f(L.dfz) && finite_f(L.r.dx) && finite_f(L.r.dy) &&
+                      finite_f(L.r.dz) && finite_f(L.r.ox) && finite_f(L.r.oy) && finite_f(L.r.oz);
+    const bool tame = safe && sc.leaf_cull && (fabsf(L.r.dx) + fabsf(L.r.dy) + fabsf(L.r.dz)) <= 2.0f &&
+                      (fabsf(L.r.ox - sc.tame_c[0]) + fabsf(L.r.oy - sc.tame_c[1]) + fabsf(L.r.oz - sc.tame_c[2])) <= sc.tame_r;
+    L.rf = (L.r.dx > 0.0f ? 1u : 0u) | (L.r.dy > 0.0f ? 2u : 0u) | (L.r.dz > 0.0f ? 4u : 0u) | (safe ? 0u : kRfUnsafe) | (tame ? kRfTame : 0u);
     L.tmin = 0.0f; L.tmax = 0.0f;
     if (sc.root_is_leaf) {                       // tree = Leaf: no box test at all (BIH.hs:105)
         L.child = 0u; L.i = (int)sc.n_tris - 1;
@@ -511,8 +531,8 @@ SQT_HD void start_ray(const SceneView &sc, TravLane &L, Counters *cn) {
         return;
     }
     if (!slab_iv(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], L.r, L.dfx,
-                 L.dfy, L.dfz, L.safe, L.tmin, L.tmax)) { finish_ray(sc, L, LaneRay(L)); return; }          // BIH.hs:112 at the root
-    L.child = 0u; L.state = ST_DESC;
+                 L.dfy, L.dfz, safe, L.tmin, L.tmax)) { finish_ray(sc, L, LaneRay(L)); return; }          // BIH.hs:112 at the root
+    L.child = kTight; L.state = ST_DESC;              // the root's record is always looked at (tame rays)
 }
 
 // Entering Leaf `L.child` (index into the leaf array) (BIH.hs:105-109).
@@ -535,7 +555,7 @@ SQT_HD void enter_step(const SceneView &sc, TravLane &L, const RA &ra, Counters 
     uint32_t count = w >> kLeafCountShift;
     L.cur.tri = -1;
     if (count == 0u) { L.state = ST_RET; return; }                        // empty leaf -> Nothing (BIH.hs:107)
-    if (sc.leaf_cull && L.safe) {
+    if (sc.leaf_cull && !(L.rf & kRfUnsafe)) {
         const Ray r = ra.ray();
         float dfx, dfy, dfz;
         ra.dfv(dfx, dfy, dfz);
@@ -593,49 +613,58 @@ SQT_COLD float4 desc_children_literal(const float4 *boxes, uint32_t node, float 
 template <bool COUNT, int STRIDE = 1, class RA>
 SQT_HD void desc_step(const SceneView &sc, TravLane &L, const RA &ra, Counters *cn) {
     const uint32_t node = L.child & kIdxMask;
-    const float4 q = SQT_LDG4(sc.nodes + (size_t)node);                    // issued before the slab test so that both loads overlap
-    if ((L.child & kTight) && L.tame) {
-        // Subtree slab (not in the reference; exact like the leaf culling): every triangle below this
-        // Branch lies inside its tight box, and an accepted hit lies within the a-priori margin of its triangle.  One axis of
-        // that box, enlarged by the margin, is intersected with the interval the ray carries: the interval only shrinks, so a
-        // child test below can only change from "hit" to "miss" -- and only where no triangle could have been accepted.
-        const float4 sl = SQT_LDG4(sc.slabs + (size_t)node);
-        const int sax = (int)(f2u(sl.w) & 3u);
-        const float o = ra.o(sax), df = ra.df(sax);
-        const float t1 = (sl.x - o) * df, t2 = (sl.y - o) * df;
-        L.tmin = SQT_FMAX(L.tmin, SQT_FMIN(t1, t2));
-        L.tmax = SQT_FMIN(L.tmax, SQT_FMAX(t1, t2));
-        if (!(L.tmax > 0.0f && L.tmin < L.tmax)) {
-            if (COUNT) cn->leaves_culled += 1;
-            L.cur.tri = -1; L.state = ST_RET;
-            return;
-        }
-    }
+    const float4 q = SQT_LDG4(sc.nodes + (size_t)node);
+    const bool slabs = (L.child & L.rf & kTight) != 0u;                     // known from the reference: both loads go out together
+    float4 cs;
+#ifdef __CUDA_ARCH__
+    asm("" : "=f"(cs.x), "=f"(cs.y), "=f"(cs.z), "=f"(cs.w));                  // only read under `slabs`: no registers to initialise
+#else
+    cs = q;
+#endif
+    if (slabs) cs = SQT_LDG4(sc.slabs + (size_t)node);
     const uint32_t lb = f2u(q.z), rb = f2u(q.w);
     const int ax = (int)((lb >> kAxisShift) & 3u);
-    const bool ltr = ((L.sgn >> ax) & 1u) != 0u;                            // BIH.hs:127
+    const bool ltr = ((L.rf >> ax) & 1u) != 0u;                             // BIH.hs:127
     if (COUNT) { cn->branch_visits += 1; cn->child_box_tests += 2; }
     float n_min, n_max, f_min, f_max;                                       // intervals of the near / far child
-    bool hit_n, hit_f;
-    if (L.safe && !(lb & kSlow)) {
+    if (((lb | L.rf) & kSlow) == 0u) {                                      // node not kSlow and ray not kRfUnsafe
         const float o = ra.o(ax), df = ra.df(ax);
         const float tl = XMUL(XSUB(q.x, o), df), tr = XMUL(XSUB(q.y, o), df);
         n_min = L.tmin; n_max = SQT_FMIN(L.tmax, ltr ? tl : tr);
         f_min = SQT_FMAX(L.tmin, ltr ? tr : tl); f_max = L.tmax;
-        hit_n = n_max > 0.0f && n_min < n_max;
-        hit_f = f_max > 0.0f && f_min < f_max;
     } else {
         const Ray r = ra.ray();
         float dfx, dfy, dfz;
         ra.dfv(dfx, dfy, dfz);
-        const float4 iv = desc_children_literal(sc.boxes, node, q.x, q.y, ax, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, dfx, dfy, dfz, L.safe);
-        const bool hit_l = iv.y > 0.0f && iv.x < iv.y, hit_r = iv.w > 0.0f && iv.z < iv.w;      // Geometry.hs:177
-        hit_n = ltr ? hit_l : hit_r; hit_f = ltr ? hit_r : hit_l;
+        const float4 iv = desc_children_literal(sc.boxes, node, q.x, q.y, ax, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, dfx, dfy, dfz, !(L.rf & kRfUnsafe));
         n_min = ltr ? iv.x : iv.z; n_max = ltr ? iv.y : iv.w;
         f_min = ltr ? iv.z : iv.x; f_max = ltr ? iv.w : iv.y;
     }
-    if (!(hit_n || hit_f)) { L.cur.tri = -1; L.state = ST_RET; return; }
     const uint32_t nref = (ltr ? lb : rb) & (kLeaf | kTight | kIdxMask), fref = (ltr ? rb : lb) & (kLeaf | kTight | kIdxMask);
+    if (slabs) {
+        // Subtree / leaf slabs (not in the reference; exact like the leaf culling): every triangle below
+        // a child lies inside the child's tight box, and an accepted hit lies within the a-priori margin of its triangle.  One
+        // axis of that box, enlarged by the margin, is intersected with the child's interval: the interval only shrinks, so
+        // the child's test -- and every test below it -- can only change from "hit" to "miss", and only where no triangle could
+        // have been accepted.  A child that fails is treated like a child whose box the ray misses: the reference would have
+        // visited it and got Nothing, which changes none of BIH.hs:113-126.
+        const float n_lo = ltr ? cs.x : cs.z, n_hi = ltr ? cs.y : cs.w, f_lo = ltr ? cs.z : cs.x, f_hi = ltr ? cs.w : cs.y;
+        const uint32_t ncode = f2u(n_lo) & 3u, fcode = f2u(f_lo) & 3u;
+        if (COUNT) cn->leaves_culled += (n_max > 0.0f && n_min < n_max ? 1u : 0u) + (f_max > 0.0f && f_min < f_max ? 1u : 0u);
+        if (ncode != kSlabNone) {
+            const float o = ra.o((int)ncode), df = ra.df((int)ncode);
+            const float t1 = (n_lo - o) * df, t2 = (n_hi - o) * df;
+            n_min = SQT_FMAX(n_min, SQT_FMIN(t1, t2)); n_max = SQT_FMIN(n_max, SQT_FMAX(t1, t2));
+        }
+        if (fcode != kSlabNone) {
+            const float o = ra.o((int)fcode), df = ra.df((int)fcode);
+            const float t1 = (f_lo - o) * df, t2 = (f_hi - o) * df;
+            f_min = SQT_FMAX(f_min, SQT_FMIN(t1, t2)); f_max = SQT_FMIN(f_max, SQT_FMAX(t1, t2));
+        }
+        if (COUNT) cn->leaves_culled -= (n_max > 0.0f && n_min < n_max ? 1u : 0u) + (f_max > 0.0f && f_min < f_max ? 1u : 0u);
+    }
+    const bool hit_n = n_max > 0.0f && n_min < n_max, hit_f = f_max > 0.0f && f_min < f_max;       // Geometry.hs:177
+    if (!(hit_n || hit_f)) { L.cur.tri = -1; L.state = ST_RET; return; }
     if (hit_n && hit_f) {                       // phase A entry: the far child, its interval, the plane isClose compares with
         float4 e;
         e.x = u2f(fref | ((uint32_t)ax << kAxisShift)); e.y = f_min; e.z = f_max; e.w = ltr ? q.y : q.x;      // rmin : lmax
@@ -697,7 +726,7 @@ SQT_HD void ret_step(const SceneView &sc, TravLane &L, const RA &ra) {
         }
         if (L.cur.tri >= 0) {
             const int ax = (int)((w >> kAxisShift) & 3u);
-            const bool ltr = ((L.sgn >> ax) & 1u) != 0u;                    // BIH.hs:127: the near child was left iff leftToRight
+            const bool ltr = ((L.rf >> ax) & 1u) != 0u;                     // BIH.hs:127: the near child was left iff leftToRight
             const float p = XADD(ra.o(ax), XMUL(L.cur.t, ra.d(ax)));        // intersectPoint on ax
             const bool close = ltr ? (p < e.w) : (p > e.w);                 // BIH.hs:121-123
             if (close) { L.sp -= 1; continue; }

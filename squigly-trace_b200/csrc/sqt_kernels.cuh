@@ -8,7 +8,7 @@
 //   k_accumulate       : adds a round's samples to the per-pixel sums in sample order (Lib.hs:88)
 //   k_raycast          : --cast mode (Lib.hs:141-151)
 //   k_tonemap          : mean + rgbFloatToPixelRGB (Lib.hs:88-104)
-//   k_leaf_records, k_check_materials, k_branch_tight, k_child_slabs : scene upload (leaf records from the triangles; material
+//   k_leaf_records, k_check_materials, k_branch_tight, k_child_slabs, k_flag_slabs : scene upload (leaf records from the triangles; material
 //                        index validation; tight subtree slabs bottom-up)
 //   k_fp32_peak, k_l2_read : roofline denominators measured on the device
 #pragma once
@@ -135,7 +135,7 @@ __device__ __forceinline__ void warp_loop(const SceneView &sc, Policy &pol, Coun
     float4 stack[kStackEntries];
     TravLane L;
     L.stack = stack;
-    L.state = ST_DONE; L.sp = 0; L.i = 0; L.child = 0u; L.tmin = 0.0f; L.tmax = 0.0f; L.safe = true; L.sgn = 0u;
+    L.state = ST_DONE; L.sp = 0; L.i = 0; L.child = 0u; L.tmin = 0.0f; L.tmax = 0.0f; L.rf = 0u;
     L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
     L.dfx = L.dfy = L.dfz = 0.0f;
     L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
@@ -284,7 +284,7 @@ struct PoolTune { int burst_t, t_leave, c_min; };
 
 // 16 words = 64 B per ray in shared memory; the first nine are what PoolRay reads.  PF_TMIN holds the interval's lower
 // end while the ray descends and `i` (triangles left - 1) for a ray that starts inside a leaf (root leaf);
-// PF_FLAGS = state | safe << 8 | tame << 9 | sgn << 16 | sp << 24.
+// PF_FLAGS = TravLane::rf (bits 0-2, 27, 30) | state << 4 | sp << 8.
 enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_TMIN, PF_TMAX, PF_CTRI, PF_CT, PF_CDIST,
        PF_FLAGS, PF_WORDS };
 enum { KT = 0, KL = 1, KR = 2, KS = 3, KNONE = 4 };
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int slot = wbase + lane + 32 * k;
-        PW(PF_FLAGS, slot) = (uint32_t)ST_DONE;
+        PW(PF_FLAGS, slot) = (uint32_t)ST_DONE << 4;
         PW(PF_CTRI, slot) = 0xffffffffu;
         queue[KR * P + lane + 32 * k] = (uint8_t)(lane + 32 * k);
         gpath[2 * (gbase + slot)] = make_uint4(0u, 0u, 0u, 0u);
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             if (act) {
                 L.child = PW(PF_CHILD, slot); L.tmin = u2f(PW(PF_TMIN, slot)); L.tmax = u2f(PW(PF_TMAX, slot));
                 fl = PW(PF_FLAGS, slot);
-                L.state = (int)(fl & 0xffu); L.safe = ((fl >> 8) & 1u) != 0u; L.tame = ((fl >> 9) & 1u) != 0u; L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
+                L.state = (int)((fl >> 4) & 15u); L.rf = fl; L.sp = (int)((fl >> 8) & 0xffu);
             }
             for (int b = 0; b < tn.burst_t; ++b) {
                 if (COUNT) { dbg_desc[b < 7 ? b : 7] += __popc(__ballot_sync(FULL, L.state == ST_DESC)); }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             if (act) {
                 PW(PF_CHILD, slot) = L.child; PW(PF_TMIN, slot) = f2u(L.tmin); PW(PF_TMAX, slot) = f2u(L.tmax);
                 if (L.state == ST_RET) PW(PF_CTRI, slot) = 0xffffffffu;     // desc_step: the subtree returned Nothing
-                PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
+                PW(PF_FLAGS, slot) = (fl & 0xffff000fu) | ((uint32_t)L.state << 4) | ((uint32_t)L.sp << 8);
             }
         } else if (kind == KL) {
             // ---- leaf work.  Stage 1: enter the leaf (record fetch + conservative culling)
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             if (act) {
                 fl = PW(PF_FLAGS, slot);
                 L.child = PW(PF_CHILD, slot);
-                L.safe = ((fl >> 8) & 1u) != 0u;
-                L.state = (int)(fl & 0xffu);
+                L.rf = fl;
+                L.state = (int)((fl >> 4) & 15u);
                 L.i = (int)PW(PF_TMIN, slot);                               // only meaningful for a ray that started inside a (root) leaf
                 L.cur.tri = (int)PW(PF_CTRI, slot);
                 if (L.state == ST_ENTER) {
@@ -498,13 +498,13 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             L.stack = cstack + slot;
             if (act) {
                 L.cur.tri = (int)PW(PF_CTRI, slot); L.cur.t = u2f(PW(PF_CT, slot)); L.cur.dist = u2f(PW(PF_CDIST, slot));
-                L.sgn = (fl >> 16) & 7u; L.sp = (int)(fl >> 24);
+                L.rf = fl; L.sp = (int)((fl >> 8) & 0xffu);
                 L.tmin = 0.0f; L.tmax = 0.0f; L.child = 0u;
                 L.state = ST_RET;
                 ret_step<PT>(sc, L, ra);
                 PW(PF_CHILD, slot) = L.child; PW(PF_TMIN, slot) = f2u(L.tmin); PW(PF_TMAX, slot) = f2u(L.tmax);
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
-                PW(PF_FLAGS, slot) = (fl & 0x00ffff00u) | (uint32_t)L.state | ((uint32_t)L.sp << 24);
+                PW(PF_FLAGS, slot) = (fl & 0xffff000fu) | ((uint32_t)L.state << 4) | ((uint32_t)L.sp << 8);
             }
         } else if (kind == KS) {
             // ---- (extension) fold the analytic spheres into the BIH result of every gathered ray (sphere_step)
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 L.state = ST_SPH;
                 sphere_step(sc, L, ra);
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
-                PW(PF_FLAGS, slot) = (fl & ~0xffu) | (uint32_t)L.state;
+                PW(PF_FLAGS, slot) = (fl & ~0xf0u) | ((uint32_t)L.state << 4);
             }
         } else {
             // ---- regeneration: consume the finished hit, shade, start the next ray (or the next sample); staged, all
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             PathRay q;
             path_ray_init(q);
             uint4 *gp = gpath + 2 * (gbase + slot);
-            L.dfx = L.dfy = L.dfz = 0.0f; L.child = 0u; L.tmin = 0.0f; L.tmax = 0.0f; L.i = 0; L.sp = 0; L.safe = true; L.sgn = 0u;
+            L.dfx = L.dfy = L.dfz = 0.0f; L.child = 0u; L.tmin = 0.0f; L.tmax = 0.0f; L.i = 0; L.sp = 0; L.rf = 0u;
             L.r.ox = L.r.oy = L.r.oz = L.r.dx = L.r.dy = L.r.dz = 0.0f;
             L.cur.tri = -1; L.cur.t = 0.0f; L.cur.dist = 0.0f;
             if (act) {
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 PW(PF_DFX, slot) = f2u(L.dfx); PW(PF_DFY, slot) = f2u(L.dfy); PW(PF_DFZ, slot) = f2u(L.dfz);
                 PW(PF_CHILD, slot) = L.child; PW(PF_TMIN, slot) = L.state == ST_LEAF ? (uint32_t)L.i : f2u(L.tmin); PW(PF_TMAX, slot) = f2u(L.tmax);
                 PW(PF_CTRI, slot) = (uint32_t)L.cur.tri; PW(PF_CT, slot) = f2u(L.cur.t); PW(PF_CDIST, slot) = f2u(L.cur.dist);
-                PW(PF_FLAGS, slot) = (uint32_t)L.state | (L.safe ? 0x100u : 0u) | (L.tame ? 0x200u : 0u) | (L.sgn << 16) | ((uint32_t)L.sp << 24);
+                PW(PF_FLAGS, slot) = (L.rf & (7u | kRfTame | kRfUnsafe)) | ((uint32_t)L.state << 4) | ((uint32_t)L.sp << 8);
                 gp[0] = make_uint4(q.sidx, (uint32_t)q.j, (uint32_t)q.stream, (uint32_t)(q.stream >> 32));
                 gp[1] = make_uint4(f2u(q.saved_r), (uint32_t)(q.saved_j + 1) | (q.any_emit ? 0x10000u : 0u) | (q.in_flight ? 0x20000u : 0u), 0u, 0u);
             }
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(256) k_check_materials(const float4 *__restric
 }
 
 // scene upload, subtree slabs (sqt_core.cuh "subtree slabs"): tight records bottom-up, one launch per tree level (the
-// branches of a level only read records of deeper levels and of leaves), then every branch flags its branch children
+// branches of a level only read records of deeper levels and of leaves), then every branch flags the children whose slab is worth a test
 __global__ void __launch_bounds__(256) k_branch_tight(const uint32_t *__restrict__ level_nodes, uint32_t n, const float4 *__restrict__ nodes,
                                                       const float4 *__restrict__ leaves, float4 *tight) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -635,8 +635,34 @@ __global__ void __launch_bounds__(256) k_branch_tight(const uint32_t *__restrict
     const TightRec r = tight_union(c[0], c[1]);
     tight[2 * (size_t)b] = r.t0; tight[2 * (size_t)b + 1] = r.t1;
 }
-__global__ void __launch_bounds__(256) k_child_slabs(float4 *nodes, uint32_t n_branches, const float4 *__restrict__ boxes, const float4 *__restrict__ tight,
-                                                     float s_max, float c_max, float ratio_max, float4 *__restrict__ slabs) {
+__global__ void __launch_bounds__(256) k_child_slabs(const float4 *__restrict__ nodes, uint32_t n_branches, const float4 *__restrict__ boxes,
+                                                     const float4 *__restrict__ tight, const float4 *__restrict__ leaves, float s_max, float c_max,
+                                                     float ratio_max, float ratio_max_leaf, float4 *__restrict__ slabs) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_branches) return;
+    const float4 q = nodes[b];
+    const uint32_t w[2] = {__float_as_uint(q.z), __float_as_uint(q.w)};
+    const float4 p0 = boxes[2 * (size_t)b], p1 = boxes[2 * (size_t)b + 1];
+    const int ax = (int)((w[0] >> kAxisShift) & 3u);
+    float4 sl[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t c = w[k] & kIdxMask;
+        bool use;
+        if (w[k] & kLeaf) {
+            float4 c0, c1;
+            clip_child_box(p0, p1, ax, q.x, q.y, k, c0, c1);
+            use = make_slab(tight_of_leaf(leaves, c), c0, c1, s_max, c_max, ratio_max_leaf, sl[k]);
+        } else {
+            TightRec t; t.t0 = tight[2 * (size_t)c]; t.t1 = tight[2 * (size_t)c + 1];
+            use = make_slab(t, boxes[2 * (size_t)c], boxes[2 * (size_t)c + 1], s_max, c_max, ratio_max, sl[k]);
+        }
+        sl[k].x = pack_slab_lo(sl[k].x, use ? (__float_as_uint(sl[k].w) & 3u) : kSlabNone);
+    }
+    slabs[b] = make_float4(sl[0].x, sl[0].y, sl[1].x, sl[1].y);
+}
+// ... and every reference to a Branch whose record holds a usable slab is flagged kTight
+__global__ void __launch_bounds__(256) k_flag_slabs(float4 *nodes, uint32_t n_branches, const float4 *__restrict__ slabs) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_branches) return;
     float4 q = nodes[b];
@@ -644,11 +670,8 @@ __global__ void __launch_bounds__(256) k_child_slabs(float4 *nodes, uint32_t n_b
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (w[k] & kLeaf) continue;
-        const uint32_t c = w[k] & kIdxMask;
-        TightRec t; t.t0 = tight[2 * (size_t)c]; t.t1 = tight[2 * (size_t)c + 1];
-        float4 sl;
-        if (make_slab(t, boxes[2 * (size_t)c], boxes[2 * (size_t)c + 1], s_max, c_max, ratio_max, sl)) w[k] |= kTight;
-        slabs[c] = sl;
+        const float4 cs = slabs[w[k] & kIdxMask];
+        if ((__float_as_uint(cs.x) & 3u) != kSlabNone || (__float_as_uint(cs.z) & 3u) != kSlabNone) w[k] |= kTight;
     }
     q.z = __uint_as_float(w[0]); q.w = __uint_as_float(w[1]);
     nodes[b] = q;

@@ -164,26 +164,43 @@ inline int build_device_layout(const sqt_scene_desc &desc, DeviceLayout &out, st
     return SQT_OK;
 }
 
-constexpr float kSlabRatioMax = 0.7f;     // a slab is tested when it is at most this fraction of the clipped box on its axis
+constexpr float kSlabRatioMax = 0.7f, kSlabRatioMaxLeaf = 0.7f;     // a subtree's / leaf's slab is tested when it is at most this fraction of the clipped box on its axis
 // Host version of what k_branch_tight + k_child_slabs do on the device (tests/emu): tight records bottom-up, then every
-// Branch decides for each Branch child whether its slab is worth a test and flags the reference (kTight).
-inline void compute_slabs_host(DeviceLayout &lay, const std::vector<float4> &leaves, std::vector<float4> &slabs, float ratio_max = kSlabRatioMax) {
+// Branch decides for each child (Branch or Leaf) whether its slab is worth a test (code in the slab record), and references to Branches with such a slab are flagged kTight.
+inline void compute_slabs_host(DeviceLayout &lay, const std::vector<float4> &leaves, std::vector<float4> &slabs, float ratio_max = kSlabRatioMax, float ratio_max_leaf = kSlabRatioMaxLeaf) {
     const size_t nb = lay.n_branches;
     std::vector<TightRec> tight(nb ? nb : 1);
-    slabs.assign(nb ? nb : 1, mk4(0, 0, 2.0f, 0));
+    slabs.assign(nb ? nb : 1, mk4(u2f(kSlabNone), 0, u2f(kSlabNone), 0));
     auto child = [&](uint32_t ref) { return (ref & kLeaf) ? tight_of_leaf(leaves.data(), ref & kIdxMask) : tight[ref & kIdxMask]; };
     for (size_t i = lay.branch_order.size(); i-- > 0;) {
         const uint32_t b = lay.branch_order[i];
         tight[b] = tight_union(child(f2u(lay.nodes[b].z)), child(f2u(lay.nodes[b].w)));
     }
     for (size_t b = 0; b < nb; ++b) {
+        const float4 q = lay.nodes[b];
+        const uint32_t w[2] = {f2u(q.z), f2u(q.w)};
+        const int ax = (int)((w[0] >> kAxisShift) & 3u);
+        float4 sl[2];
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t k = w[c] & kIdxMask;
+            bool use;
+            if (w[c] & kLeaf) {
+                float4 c0, c1;
+                clip_child_box(lay.boxes[2 * b], lay.boxes[2 * b + 1], ax, q.x, q.y, c, c0, c1);
+                use = make_slab(tight_of_leaf(leaves.data(), k), c0, c1, lay.s_max, lay.c_max, ratio_max_leaf, sl[c]);
+            } else {
+                use = make_slab(tight[k], lay.boxes[2 * (size_t)k], lay.boxes[2 * (size_t)k + 1], lay.s_max, lay.c_max, ratio_max, sl[c]);
+            }
+            sl[c].x = pack_slab_lo(sl[c].x, use ? (f2u(sl[c].w) & 3u) : kSlabNone);
+        }
+        slabs[b] = mk4(sl[0].x, sl[0].y, sl[1].x, sl[1].y);
+    }
+    for (size_t b = 0; b < nb; ++b) {
         uint32_t w[2] = {f2u(lay.nodes[b].z), f2u(lay.nodes[b].w)};
         for (int c = 0; c < 2; ++c) {
             if (w[c] & kLeaf) continue;
-            const uint32_t k = w[c] & kIdxMask;
-            float4 sl;
-            if (make_slab(tight[k], lay.boxes[2 * (size_t)k], lay.boxes[2 * (size_t)k + 1], lay.s_max, lay.c_max, ratio_max, sl)) w[c] |= kTight;
-            slabs[k] = sl;
+            const float4 cs = slabs[w[c] & kIdxMask];
+            if ((f2u(cs.x) & 3u) != kSlabNone || (f2u(cs.z) & 3u) != kSlabNone) w[c] |= kTight;
         }
         lay.nodes[b].z = u2f(w[0]); lay.nodes[b].w = u2f(w[1]);
     }

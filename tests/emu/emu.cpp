@@ -65,7 +65,8 @@ int emu_height(emu_scene *s) { return (int)s->lay.height; }
 int emu_slow_nodes(emu_scene *s) { return (int)s->lay.n_slow; }
 int emu_tight_children(emu_scene *s) {
     int n = 0;
-    for (size_t b = 0; b < s->lay.n_branches; ++b) n += ((f2u(s->lay.nodes[b].z) & kTight) ? 1 : 0) + ((f2u(s->lay.nodes[b].w) & kTight) ? 1 : 0);
+    for (size_t b = 0; b < s->lay.n_branches; ++b)
+        n += ((f2u(s->slabs[b].x) & 3u) != kSlabNone ? 1 : 0) + ((f2u(s->slabs[b].z) & 3u) != kSlabNone ? 1 : 0);
     return n;
 }
 void emu_set_leaf_cull(emu_scene *s, int on) { s->view.leaf_cull = on ? 1u : 0u; }
@@ -342,7 +343,7 @@ void emu_group_cull_stats(emu_scene *s, const float *org, const float *dir, long
                     make_leaf_record(s->tris.data(), first + g0, gc, b0, b1);
                     out[3] += 1;
                     bool keep = true;
-                    if (L.safe) {
+                    if (!(L.rf & kRfUnsafe)) {
                         const Ray &r = L.r;
                         const float d1 = fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz), dfac = d1 * (1.0f + d1);
                         const float E = b1.z;
