@@ -301,7 +301,9 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
     // carve-out, the next one (196 KB) would leave 32 KB instead of 64 KB of L1 for triangles, nodes and stacks
     constexpr int AUX_WORDS = 4 * P / 4 + 64 + 8 + 8 + 32;
     const unsigned FULL = 0xffffffffu;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (the warp index comes out of a REDUX, i.e. in a uniform register: the per-warp scratch addresses derived from it are then
+    //  uniform too and are not rebuilt from SR_TID in every loop that is short of registers)
+    const int warp = (int)__reduce_max_sync(FULL, threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int wbase = warp * P;
     uint32_t *pool = pool_smem;                                                 // word f of slot g at pool[f * PT + g]
     uint32_t *aux = pool_smem + PT * PF_WORDS + warp * AUX_WORDS;
@@ -327,8 +329,9 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         gpath[2 * (gbase + slot) + 1] = make_uint4(0u, 0u, 0u, 0u);      // saved_j = -1 (stored +1), any_emit = in_flight = false
     }
     __syncwarp(FULL);
-    unsigned lt_mask;
+    unsigned lt_mask, le_mask;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(le_mask));
     // queue state, warp-uniform, one byte per kind: ring head (< P) and fill (<= P <= 128)
     unsigned q_head = 0u, q_cnt = (unsigned)P << (8 * KR);     // (P = 128 fills its byte exactly: the top byte, KS, never holds more than P)
     unsigned long long dbg_rounds[3] = {0, 0, 0}, dbg_sel[3] = {0, 0, 0}, dbg_desc[8] = {}, dbg_ret[8] = {}, dbg_leaf[4] = {};
@@ -399,8 +402,8 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             }
             __syncwarp(FULL);
             // Stage 2: all (ray, triangle) tests of the gathered rays, 32 per step.  Test p of a pass belongs to the lane
-            // whose inclusive scan first exceeds p; within a ray tests run from its last triangle to its first.  A test is
-            // first run to the `u` guard only (moller_trumbore_au); the ~18 % that survive are appended -- in test order --
+            // whose inclusive scan first exceeds p; within a ray tests run from its last triangle to its first.  A test first
+            // goes through a division-free filter for the `a` and `u` guards (moller_trumbore_au); the ~18 % that survive are appended -- in test order --
             // to a small ring in shared memory and re-run in full, 32 at a time, so that the expensive tail of
             // Moller-Trumbore (second cross product, v / t guards, point, IEEE sqrt) also executes with all lanes.
             int n_surv = 0, surv_head = 0;                                  // warp-uniform
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                     const Ray r = PoolRay(pool + oslot, PT).ray();
                     int stage;
                     hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
-                    if (COUNT) { cn.mt_pass_v += stage >= 3; cn.mt_accept += stage >= 4; }
+                    if (COUNT) { cn.mt_pass_u += stage >= 2; cn.mt_pass_v += stage >= 3; cn.mt_accept += stage >= 4; }
                 }
                 unsigned hm = __ballot_sync(FULL, hit);
                 while (hm != 0u) {                                          // fold each accepted hit into its ray, in test order
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 auto map_chunk = [&](int base, int &own_o, uint32_t &idx_o, int &oslot_o) {
                     const unsigned rel = (unsigned)(start - base);
                     const unsigned sm = __reduce_or_sync(FULL, (c > 0 && rel < 32u) ? (1u << rel) : 0u);
-                    int k = started + __popc(sm & (0xffffffffu >> (31 - lane))) - 1;
+                    int k = started + __popc(sm & le_mask) - 1;
                     started += __popc(sm);
                     if (base + lane >= total) k = 0;
                     own_o = (int)own_lane[k];
@@ -479,9 +482,9 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                     if (pr < total) {
                         const TriData d = tri_load(sc, idx);
                         const Ray r = PoolRay(pool + oslot, PT).ray();
-                        int stage;
-                        pass = moller_trumbore_au(d.a0, d.a1, d.a2, r, stage);
-                        if (COUNT) { cn.mt_pass_a += stage >= 1; cn.mt_pass_u += stage >= 2; }
+                        bool pass_a;
+                        pass = moller_trumbore_au(d.a0, d.a1, d.a2, r, pass_a);
+                        if (COUNT) cn.mt_pass_a += pass_a;
                     }
                     const unsigned pm = __ballot_sync(FULL, pass);
                     if (pass) survivors[(surv_head + n_surv + __popc(pm & lt_mask)) & 63] = idx | ((uint32_t)own << 27);

@@ -266,6 +266,25 @@ long long emu_trace_lane(emu_scene *s, const sqt_camera *cam, const sqt_render_p
     return n < cap ? n : cap;
 }
 
+// The pool kernel's division-free filter (moller_trumbore_au) against the full test, pair i = (triangle record i, ray i).
+// tri = 12 floats per record (the device layout: v0.xyz e1.x | e1.yz e2.xy | e2.z - - -).
+// out = { pairs, full test got past `u` (stage >= 2), filter passed, VIOLATIONS: full test got past `u` but the filter said no,
+//         `a` guard disagreements }
+void emu_filter_stats(const float *tri, const float *org, const float *dir, long long n, unsigned long long *out) {
+    for (int k = 0; k < 5; ++k) out[k] = 0;
+    for (long long i = 0; i < n; ++i) {
+        const float *q = tri + 12 * i;
+        const float4 a0 = mk4(q[0], q[1], q[2], q[3]), a1 = mk4(q[4], q[5], q[6], q[7]), a2 = mk4(q[8], q[9], q[10], q[11]);
+        const Ray r{org[3 * i], org[3 * i + 1], org[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+        float t, dist; int stage; bool pass_a;
+        moller_trumbore(a0, a1, a2, r, t, dist, stage);
+        const bool pass = moller_trumbore_au(a0, a1, a2, r, pass_a);
+        out[0] += 1; out[1] += stage >= 2; out[2] += pass;
+        if (stage >= 2 && !pass) out[3] += 1;
+        if ((stage >= 1) != pass_a) out[4] += 1;
+    }
+}
+
 // Diagnostic for DESIGN.md: how many leaf visits would a (conservatively enlarged) tight leaf bounding box reject?
 // out = { leaf visits, triangle tests, visits whose ray misses the enlarged tight box, triangle tests in those,
 //         visits with at least one accepted triangle, of those rejected by the box (must be 0) }

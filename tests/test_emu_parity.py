@@ -257,3 +257,59 @@ def test_sphere_hierarchy_gives_the_definitions_result(host_scene, camera):
     got = e.render(camera, pysqt.make_params(64, 48, 4, max_depth=6, seed=3))
     ref = osc.render(camera, O.make_params(64, 48, 4, max_depth=6, seed=3, trig=1))
     assert np.array_equal(bits(got["accum"]), bits(ref["accum"])) and np.array_equal(got["rgb8"], ref["rgb8"])
+
+
+def _filter_stats(tri12, org, dirs):
+    import ctypes as C
+    from common import emu_lib, _p
+    tri12 = np.ascontiguousarray(tri12, np.float32); org = np.ascontiguousarray(org, np.float32); dirs = np.ascontiguousarray(dirs, np.float32)
+    out = np.zeros(5, np.uint64)
+    E = emu_lib()
+    E.emu_filter_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+    E.emu_filter_stats(_p(tri12), _p(org), _p(dirs), len(org), _p(out))
+    return [int(x) for x in out]
+
+
+def test_triangle_filter_is_conservative():
+    """The pool kernel's division-free a/u filter (moller_trumbore_au) never rejects a pair the full test takes past `u`,
+    agrees with it on the `a` guard, and lets through hardly anything else -- on ordinary pairs, on pairs whose u sits
+    on 0 or 1 to the last bit, on extreme scales and on non-finite input."""
+    rng = np.random.default_rng(77)
+    n = 400_000
+    v0 = rng.uniform(-1, 1, (n, 3)); e1 = rng.uniform(-1, 1, (n, 3)) * 0.5; e2 = rng.uniform(-1, 1, (n, 3)) * 0.5
+    # aim at a point u*e1 + v*e2 with u spread around [0, 1], a third of them exactly on u = 0 or u = 1
+    u = rng.uniform(-0.5, 1.5, n); v = rng.uniform(-0.2, 1.0, n)
+    kind = rng.integers(0, 3, n)
+    u = np.where(kind == 1, 0.0, np.where(kind == 2, 1.0, u))
+    target = v0 + u[:, None] * e1 + v[:, None] * e2
+    org = target + rng.normal(size=(n, 3)) * rng.choice([0.01, 1.0, 30.0], (n, 1))
+    d = target - org
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d *= rng.choice([1.0, 1.0, 1e-3, 1e3], (n, 1))
+    tri = np.zeros((n, 12), np.float32)
+    tri[:, 0:3] = v0; tri[:, 3:6] = e1; tri[:, 6:9] = e2
+    pairs, exact, filt, viol, amis = _filter_stats(tri, org, d)
+    assert pairs == n and viol == 0 and amis == 0
+    assert exact > n // 4
+    o = kind == 0                                       # the ordinary pairs: the filter is as selective as the guard itself
+    _, ex_o, f_o, _, _ = _filter_stats(tri[o], org[o], d[o])
+    assert ex_o <= f_o <= ex_o + max(20, ex_o // 5000), (ex_o, f_o)
+    # extreme scales: everything multiplied by 2^k (the geometry is scale invariant up to the eps guards)
+    for k in (-60, -30, -12, 12, 30, 60):
+        sc = np.float32(2.0) ** k
+        p2, ex2, f2, viol2, amis2 = _filter_stats(tri * sc, (org * sc).astype(np.float32), d.astype(np.float32))
+        assert viol2 == 0 and amis2 == 0, (k, viol2, amis2)
+    # non-finite and zero input anywhere
+    m = 60_000
+    sub = slice(0, m)
+    bad = np.array([np.inf, -np.inf, np.nan, 0.0, -0.0, 1e-45, -1e-45, 3e38], np.float32)
+    tri_b = tri[sub].copy(); org_b = org[sub].astype(np.float32).copy(); d_b = d[sub].astype(np.float32).copy()
+    where = rng.integers(0, 15, m)
+    val = bad[rng.integers(0, len(bad), m)]
+    for i in range(m):
+        w = where[i]
+        if w < 9: tri_b[i, w] = val[i]
+        elif w < 12: org_b[i, w - 9] = val[i]
+        else: d_b[i, w - 12] = val[i]
+    p3, ex3, f3, viol3, amis3 = _filter_stats(tri_b, org_b, d_b)
+    assert viol3 == 0 and amis3 == 0, (viol3, amis3)
