@@ -5,7 +5,7 @@ rep = sys.argv[1]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-# function line ranges from the sources (top-level SQT_HD / __device__ / __global__ definitions)
+# function line ranges from the sources (top-level SQT_HD / __device__ / __global__ definitions and structs)
 ranges = {}
 for f in ("sqt_core.cuh", "sqt_paths.cuh", "sqt_kernels.cuh", "sqt_backend.cu"):
     src = open(os.path.join(ROOT, "squigly-trace_b200", "csrc", f)).read().splitlines()
@@ -13,6 +13,8 @@ for f in ("sqt_core.cuh", "sqt_paths.cuh", "sqt_kernels.cuh", "sqt_backend.cu"):
     for i, l in enumerate(src, 1):
         m = re.match(r"^(?:template.*>\s*)?(?:SQT_HD|__device__|__global__|static|inline).*?\b([A-Za-z_0-9]+)\s*\(", l)
         if m and not l.startswith(" "): starts.append((i, m.group(1)))
+        m = re.match(r"^struct\s+([A-Za-z_0-9]+)\s*\{", l)                # accessor structs (LaneRay, PoolRay): their methods are one-liners inside
+        if m: starts.append((i, "struct " + m.group(1)))
     for (a, n), nxt in zip(starts, starts[1:] + [(len(src) + 1, "")]): ranges.setdefault(f, []).append((a, nxt[0] - 1, n))
 def func(f, ln):
     for a, b, n in ranges.get(f, []):
