@@ -278,6 +278,32 @@ __global__ void __launch_bounds__(128, SQT_WL_MIN_BLOCKS) k_paths(SceneView sc, 
 #ifndef SQT_POOL_MIN_BLOCKS
 #define SQT_POOL_MIN_BLOCKS 8
 #endif
+// The pool is read and written by 32-bit shared-memory address.  A generic pointer into shared memory makes the compiler rebuild
+// the shared window base (S2UR SR_CgaCtaId, UMOV, ULEA, LEA) wherever it is short of registers -- inside the branch visit, in
+// every chunk of the leaf phase -- and that sequence sits in front of the LDS it feeds.  The base is taken once, passed through a
+// REDUX so that it lives in a uniform register, and every access is `[lane register + uniform base + immediate]`.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+struct SharedWord {                       // PW(f, g) = x ; x = PW(f, g)
+    uint32_t a;
+    __device__ __forceinline__ operator uint32_t() const { return lds32(a); }
+    __device__ __forceinline__ void operator=(uint32_t v) const { sts32(a, v); }
+    SharedWord &operator=(const SharedWord &) = delete;
+};
+// PoolRay (sqt_core.cuh) by shared address: word k of the slot at a + k * STRIDE_B
+template <int STRIDE_B>
+struct PoolRayS {
+    uint32_t a;
+    __device__ __forceinline__ float f(int k) const { return __uint_as_float(lds32(a + (uint32_t)(k * STRIDE_B))); }
+    __device__ __forceinline__ float o(int ax) const { return f(ax); }
+    __device__ __forceinline__ float d(int ax) const { return f(3 + ax); }
+    __device__ __forceinline__ float df(int ax) const { return f(6 + ax); }
+    __device__ __forceinline__ Ray ray() const { Ray r; r.ox = f(0); r.oy = f(1); r.oz = f(2); r.dx = f(3); r.dy = f(4); r.dz = f(5); return r; }
+    __device__ __forceinline__ void dfv(float &x, float &y, float &z) const { x = f(6); y = f(7); z = f(8); }
+};
+
 // burst_t: traversal steps per T round (at most); t_leave: end the burst early once at most this many lanes still traverse;
 // c_min: serve the regeneration queue only when it holds at least this many rays (or nothing else can run)
 struct PoolTune { int burst_t, t_leave, c_min; };
@@ -305,16 +331,17 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
     //  uniform too and are not rebuilt from SR_TID in every loop that is short of registers)
     const int warp = (int)__reduce_max_sync(FULL, threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int wbase = warp * P;
-    uint32_t *pool = pool_smem;                                                 // word f of slot g at pool[f * PT + g]
-    uint32_t *aux = pool_smem + PT * PF_WORDS + warp * AUX_WORDS;
-    uint8_t *queue = (uint8_t *)aux;                                            // queue[k * P + i], k = KT, KL, KR, KS: rings of slot ids (g - wbase)
-    uint32_t *survivors = aux + 4 * P / 4;                                      // ring of 64 (triangle | gathering lane << 27)
-    uint8_t *lane_slot = (uint8_t *)(survivors + 64);                           // leaf round: the slot (g - wbase) each lane gathered
-    uint8_t *own_lane = lane_slot + 32;                                         // leaf round, per owner rank: its lane ...
-    uint32_t *own_tri = survivors + 64 + 16;                                    // ... and triangle of its test 0 + that test's position
+    const uint32_t sbase = __reduce_max_sync(FULL, (uint32_t)__cvta_generic_to_shared(pool_smem));      // word f of slot g at sbase + 4 (f PT + g)
+    // per-warp scratch (shared addresses, warp-uniform):
+    const uint32_t a_queue = sbase + 4u * (uint32_t)(PT * PF_WORDS + warp * AUX_WORDS);   // bytes: queue[k * P + i], k = KT, KL, KR, KS: rings of slot ids (g - wbase)
+    const uint32_t a_surv = a_queue + 4u * P;                                   // words: ring of 64 (triangle | gathering lane << 27)
+    const uint32_t a_lane_slot = a_surv + 256u;                                 // bytes: leaf round, the slot (g - wbase) each lane gathered
+    const uint32_t a_own_lane = a_lane_slot + 32u;                              // bytes: leaf round, per owner rank: its lane ...
+    const uint32_t a_own_tri = a_lane_slot + 64u;                               // words: ... and triangle of its test 0 + that test's position
     const int gbase = (int)(blockIdx.x * PT);                                   // global slot = gbase + g (< 2^31: a few hundred thousand exist)
     float4 *cstack = gstack + (size_t)gbase * (size_t)stack_depth;              // entry e of slot g at cstack[e * PT + g]
-#define PW(f, g) pool[(f) * PT + (g)]
+#define PW(f, g) SharedWord{sbase + 4u * (uint32_t)((f) * PT + (g))}
+    typedef PoolRayS<4 * PT> SlotRay;
     Counters cn = {};
     PathStats st = {0, 0, 0};
     if (rd.pixel_list) rd.n_slots = (long long)ds->n_hit;
@@ -324,7 +351,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         const int slot = wbase + lane + 32 * k;
         PW(PF_FLAGS, slot) = (uint32_t)ST_DONE << 4;
         PW(PF_CTRI, slot) = 0xffffffffu;
-        queue[KR * P + lane + 32 * k] = (uint8_t)(lane + 32 * k);
+        sts8(a_queue + (uint32_t)(KR * P + lane + 32 * k), (uint32_t)(lane + 32 * k));
         gpath[2 * (gbase + slot)] = make_uint4(0u, 0u, 0u, 0u);
         gpath[2 * (gbase + slot) + 1] = make_uint4(0u, 0u, 0u, 0u);      // saved_j = -1 (stored +1), any_emit = in_flight = false
     }
@@ -351,14 +378,14 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
         {
             const int sh = 8 * kind;
             const unsigned h = (q_head >> sh) & 0xffu;
-            if (act) slot = wbase + (int)queue[kind * P + ((h + lane) & (P - 1))];
+            if (act) slot = wbase + (int)lds8(a_queue + (uint32_t)(kind * P) + ((h + (unsigned)lane) & (unsigned)(P - 1)));
             q_head = (q_head & ~(0xffu << sh)) | (((h + n_sel) & (P - 1)) << sh);
             q_cnt -= (unsigned)n_sel << sh;
         }
         TravLane L;
         L.stack = nullptr;
         L.state = ST_EXIT;
-        const PoolRay ra(pool + slot, PT);
+        const SlotRay ra{sbase + 4u * (uint32_t)slot};
         if (COUNT && kind < 3) { dbg_rounds[kind] += 1; dbg_sel[kind] += n_sel; }
         if (kind == KT) {
             // ---- traversal steps: branch visits only.  Stack pops happen at the end of the leaf round (stage 3), so the rare
@@ -386,7 +413,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             uint32_t fl = 0u;
             uint32_t first = 0u;
             int rem = 0;                                                    // triangles of this lane's ray still to test
-            lane_slot[lane] = (uint8_t)(slot & (P - 1));
+            sts8(a_lane_slot + (uint32_t)lane, (uint32_t)(slot & (P - 1)));
             if (act) {
                 fl = PW(PF_FLAGS, slot);
                 L.child = PW(PF_CHILD, slot);
@@ -408,14 +435,14 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             // Moller-Trumbore (second cross product, v / t guards, point, IEEE sqrt) also executes with all lanes.
             int n_surv = 0, surv_head = 0;                                  // warp-uniform
             auto run_survivors = [&](int n) {
-                const uint32_t e = lane < n ? survivors[(surv_head + lane) & 63] : 0u;
-                const int oslot = wbase + (int)lane_slot[e >> 27];
+                const uint32_t e = lane < n ? lds32(a_surv + 4u * (uint32_t)((surv_head + lane) & 63)) : 0u;
+                const int oslot = wbase + (int)lds8(a_lane_slot + (e >> 27));
                 const uint32_t idx = e & kLeafFirstMask;
                 bool hit = false;
                 float t = 0.0f, dist = 0.0f;
                 if (lane < n) {
                     const TriData d = tri_load(sc, idx);
-                    const Ray r = PoolRay(pool + oslot, PT).ray();
+                    const Ray r = SlotRay{sbase + 4u * (uint32_t)oslot}.ray();
                     int stage;
                     hit = moller_trumbore(d.a0, d.a1, d.a2, r, t, dist, stage);
                     if (COUNT) { cn.mt_pass_u += stage >= 2; cn.mt_pass_v += stage >= 3; cn.mt_accept += stage >= 4; }
@@ -451,8 +478,8 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                 const unsigned om = __ballot_sync(FULL, c > 0);
                 if (c > 0) {
                     const int rank = __popc(om & lt_mask);
-                    own_lane[rank] = (uint8_t)lane;
-                    own_tri[rank] = (uint32_t)((int)first + rem - 1 + (incl - c));           // triangle of test p of this ray = that - p
+                    sts8(a_own_lane + (uint32_t)rank, (uint32_t)lane);
+                    sts32(a_own_tri + 4u * (uint32_t)rank, (uint32_t)((int)first + rem - 1 + (incl - c)));           // triangle of test p of this ray = that - p
                 }
                 __syncwarp(FULL);
                 const int start = incl - c;
@@ -465,9 +492,9 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                     int k = started + __popc(sm & le_mask) - 1;
                     started += __popc(sm);
                     if (base + lane >= total) k = 0;
-                    own_o = (int)own_lane[k];
-                    idx_o = own_tri[k] - (uint32_t)(base + lane);
-                    oslot_o = wbase + (int)lane_slot[own_o];
+                    own_o = (int)lds8(a_own_lane + (uint32_t)k);
+                    idx_o = lds32(a_own_tri + 4u * (uint32_t)k) - (uint32_t)(base + lane);
+                    oslot_o = wbase + (int)lds8(a_lane_slot + (uint32_t)own_o);
                     if (base + lane < total) prefetch_l1(sc.tris + 3 * (size_t)idx_o);
                 };
                 int own_n = 0, oslot_n = 0;
@@ -481,13 +508,13 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
                     bool pass = false;
                     if (pr < total) {
                         const TriData d = tri_load(sc, idx);
-                        const Ray r = PoolRay(pool + oslot, PT).ray();
+                        const Ray r = SlotRay{sbase + 4u * (uint32_t)oslot}.ray();
                         bool pass_a;
                         pass = moller_trumbore_au(d.a0, d.a1, d.a2, r, pass_a);
                         if (COUNT) cn.mt_pass_a += pass_a;
                     }
                     const unsigned pm = __ballot_sync(FULL, pass);
-                    if (pass) survivors[(surv_head + n_surv + __popc(pm & lt_mask)) & 63] = idx | ((uint32_t)own << 27);
+                    if (pass) sts32(a_surv + 4u * (uint32_t)((surv_head + n_surv + __popc(pm & lt_mask)) & 63), idx | ((uint32_t)own << 27));
                     n_surv += __popc(pm);
                     __syncwarp(FULL);
                     if (n_surv >= 32) run_survivors(32);
@@ -561,7 +588,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
             const unsigned add = __reduce_add_sync(FULL, nk < KNONE ? (1u << (8 * nk)) : 0u);
             if (nk < KNONE) {
                 const unsigned tail = ((q_head + q_cnt) >> (8 * nk)) & 0xffu;      // per byte: head < P, fill <= P, no carry
-                queue[nk * P + ((tail + __popc(same & lt_mask)) & (P - 1))] = (uint8_t)(slot & (P - 1));
+                sts8(a_queue + (uint32_t)(nk * P) + ((tail + (unsigned)__popc(same & lt_mask)) & (unsigned)(P - 1)), (uint32_t)(slot & (P - 1)));
             }
             q_cnt += add;
         }
