@@ -39,7 +39,7 @@ for p in (ROOT, PKG):
 
 SEED = 0
 DATA = os.path.join(ROOT, "data")
-KERNEL_VERSION = "r02-v16"         # key into profiles/r02_traffic.json (ncu DRAM bytes per k_paths_pool launch)
+KERNEL_VERSION = "r02-v17"         # key into profiles/r02_traffic.json (ncu DRAM bytes per k_paths_pool launch)
 
 
 class ClockSampler:
