@@ -154,6 +154,29 @@ def adversarial_rays(v9, seed=5, n_each=256):
     return np.concatenate(org), np.concatenate(dirs)
 
 
+def tame_boundary_rays(v9, n, seed=404):
+    """Rays around the two limits of the `tame` condition of the child slabs: (a) origins on 1-norm shells at
+    0.9 .. 1.1 of twice the root's half extent, |d|_1 between 1.9 and 2.1; (b) nearly tangential rays from inside the box;
+    (c) direction lengths over six decades.  3n rays."""
+    rng = np.random.default_rng(seed)
+    pts = np.asarray(v9, np.float64).reshape(-1, 3)
+    lo, hi = pts.min(0), pts.max(0)
+    c, h = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    u = rng.normal(size=(n, 3)); u /= np.abs(u).sum(1, keepdims=True)
+    org_a = c + u * (2.0 * h.sum()) * rng.uniform(0.9, 1.1, (n, 1))
+    tgt = c + rng.uniform(-1, 1, (n, 3)) * h
+    d_a = tgt - org_a
+    d_a /= np.abs(d_a).sum(1, keepdims=True)
+    d_a *= rng.uniform(1.9, 2.1, (n, 1))
+    org_b = c + rng.uniform(-1, 1, (n, 3)) * h
+    d_b = rng.normal(size=(n, 3)); d_b[:, int(np.argmin(h))] *= 0.02
+    d_b /= np.linalg.norm(d_b, axis=1, keepdims=True)
+    org_c = c + rng.uniform(-1.5, 1.5, (n, 3)) * h
+    d_c = rng.normal(size=(n, 3)); d_c /= np.linalg.norm(d_c, axis=1, keepdims=True)
+    d_c *= 10.0 ** rng.uniform(-3, 3, (n, 1))
+    return (np.concatenate([org_a, org_b, org_c]).astype(np.float32), np.concatenate([d_a, d_b, d_c]).astype(np.float32))
+
+
 def build_pair(v9, mat_idx, mats8):
     """(oracle scene with BIH, host scene) from the same triangle arrays."""
     osc = O.Scene.from_arrays(v9, mat_idx, mats8)

@@ -328,27 +328,9 @@ def test_child_slabs_are_exact_around_the_tame_boundary():
     emu_lib().emu_tight_children.restype = C.c_int
     emu_lib().emu_tight_children.argtypes = [C.c_void_p]
     assert emu_lib().emu_tight_children(e.h) > 1000, "the mesh is meant to have many usable slabs"
-    rng = np.random.default_rng(404)
-    lo, hi = v9.reshape(-1, 3).min(0), v9.reshape(-1, 3).max(0)
-    c, h = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    from common import tame_boundary_rays
     n = 6000
-    # (a) origins on shells at 0.9 .. 1.1 of the tame radius (1-norm distance 2 * |h|_1 from the centre), aimed at the mesh
-    u = rng.normal(size=(n, 3)); u /= np.abs(u).sum(1, keepdims=True)
-    org_a = c + u * (2.0 * h.sum()) * rng.uniform(0.9, 1.1, (n, 1))
-    tgt = c + rng.uniform(-1, 1, (n, 3)) * h
-    d_a = tgt - org_a
-    d_a /= np.abs(d_a).sum(1, keepdims=True)
-    d_a *= rng.uniform(1.9, 2.1, (n, 1))                                   # |d|_1 around 2
-    # (b) grazing rays: start just above the surface, nearly tangential
-    org_b = c + rng.uniform(-1, 1, (n, 3)) * h
-    d_b = rng.normal(size=(n, 3)); d_b[:, int(np.argmin(h))] *= 0.02
-    d_b /= np.linalg.norm(d_b, axis=1, keepdims=True)
-    # (c) direction lengths over six decades
-    org_c = c + rng.uniform(-1.5, 1.5, (n, 3)) * h
-    d_c = rng.normal(size=(n, 3)); d_c /= np.linalg.norm(d_c, axis=1, keepdims=True)
-    d_c *= 10.0 ** rng.uniform(-3, 3, (n, 1))
-    org = np.concatenate([org_a, org_b, org_c]).astype(np.float32)
-    dirs = np.concatenate([d_a, d_b, d_c]).astype(np.float32)
+    org, dirs = tame_boundary_rays(v9, n)
     want = osc.intersect_batch(org, dirs)
     got = e.intersect_batch(org, dirs)
     assert_same_hits(got, want, "child slabs on")

@@ -462,6 +462,31 @@ def test_slow_nodes_and_infinite_planes_bit_exact(gpu_ctx):
     assert_same_hits(gpu_ctx.intersect_batch(org, dirs), osc.intersect_batch(org, dirs), "infinite planes")
 
 
+def test_child_slabs_around_the_tame_boundary_bit_exact(gpu_ctx):
+    """The device side of tests/test_emu_parity.py::test_child_slabs_are_exact_around_the_tame_boundary: a height-field mesh with
+    thousands of usable child slabs; rays that switch between using and ignoring them (|d|_1 around 2, origin around twice the
+    root's half extent), grazing rays, direction lengths over six decades.  Same hits as the oracle through `k_intersect_batch`
+    and -- the pool kernel -- an image equal to the oracle's; with the culling off the visit counters equal the oracle's."""
+    from common import tame_boundary_rays
+    v9, mi, mats = scenes.subdivided_mesh(20000)
+    osc, hs = build_pair(v9, mi, mats)
+    gpu_ctx.upload(hs)
+    org, dirs = tame_boundary_rays(v9, 60_000)
+    want = osc.intersect_batch(org, dirs, counters=True)
+    got = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
+    assert_same_hits(got, want, "child slabs on")
+    with no_leaf_cull(gpu_ctx):
+        off = gpu_ctx.intersect_batch(org, dirs, want_stats=True)
+    assert_same_hits(off, want, "culling off")
+    assert off[3]["branch_visits"] == int(want[3][0]) and off[3]["tri_tests"] == int(want[3][3])
+    assert got[3]["branch_visits"] < 0.75 * off[3]["branch_visits"]
+    p = dict(max_depth=6, seed=9)
+    out = gpu_ctx.render(default_cam(), pysqt.make_params(128, 96, 8, **p))
+    ref = osc.render(default_cam(), O.make_params(128, 96, 8, trig=1, **p))
+    assert np.array_equal(bits(out["accum"]), bits(ref["accum"])) and np.array_equal(out["rgb8"], ref["rgb8"])
+    assert (ref["accum"].reshape(-1, 3) != 0).any(1).sum() > 500, "the frame is meant to show the mesh"
+
+
 def default_cam():
     return pysqt.load_camera(pysqt.ROOT + "/data/camera")
 
