@@ -266,6 +266,11 @@ long long emu_trace_lane(emu_scene *s, const sqt_camera *cam, const sqt_render_p
     return n < cap ? n : cap;
 }
 
+// pack_slab_lo for n values and codes (tests: the packed bound is never above the input and carries the code)
+void emu_pack_slab_lo(const float *lo, const unsigned *code, long long n, float *out) {
+    for (long long i = 0; i < n; ++i) out[i] = pack_slab_lo(lo[i], code[i]);
+}
+
 // The pool kernel's division-free filter (moller_trumbore_au) against the full test, pair i = (triangle record i, ray i).
 // tri = 12 floats per record (the device layout: v0.xyz e1.x | e1.yz e2.xy | e2.z - - -).
 // out = { pairs, full test got past `u` (stage >= 2), filter passed, VIOLATIONS: full test got past `u` but the filter said no,

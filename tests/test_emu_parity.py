@@ -341,3 +341,29 @@ def test_child_slabs_are_exact_around_the_tame_boundary():
     assert got_off[3]["leaves_culled"] == 0
     assert got[3]["branch_visits"] < 0.75 * got_off[3]["branch_visits"], (got[3]["branch_visits"], got_off[3]["branch_visits"])
     assert got[3]["tri_tests"] < 0.5 * got_off[3]["tri_tests"]
+
+
+def test_slab_bound_packing_is_conservative():
+    """pack_slab_lo hides the slab's axis code in the two low mantissa bits of its lower bound: the packed value must never be
+    above the input (a slab may only grow), must stay within a few ulps of it, and must give the code back."""
+    import ctypes as C
+    from common import emu_lib, _p
+    rng = np.random.default_rng(5)
+    n = 200_000
+    bits_ = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    lo = bits_.view(np.float32).copy()
+    lo[:8] = [0.0, -0.0, 1e-45, -1e-45, 1e-30, -1e-30, 3.4e38, -3.4e38]
+    lo[8:5000] = rng.uniform(-50, 50, 4992).astype(np.float32)
+    finite = np.isfinite(lo) & (np.abs(lo) < 3.0e38)
+    lo = lo[finite]
+    code = rng.integers(0, 4, len(lo)).astype(np.uint32)
+    out = np.zeros(len(lo), np.float32)
+    E = emu_lib()
+    E.emu_pack_slab_lo.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+    E.emu_pack_slab_lo(_p(lo), _p(code), len(lo), _p(out))
+    assert np.all(out <= lo)
+    assert np.array_equal(out.view(np.uint32) & 3, code)
+    big = np.abs(lo) >= 1e-30
+    ulp = np.spacing(np.abs(lo[big]))
+    assert np.all(lo[big] - out[big] <= 8 * ulp)
+    assert np.all(out[~big] >= -1.0001e-30)              # zeros and denormals become -1e-30
