@@ -367,3 +367,9 @@ def test_slab_bound_packing_is_conservative():
     ulp = np.spacing(np.abs(lo[big]))
     assert np.all(lo[big] - out[big] <= 8 * ulp)
     assert np.all(out[~big] >= -1.0001e-30)              # zeros and denormals become -1e-30
+
+
+def test_culling_fuzz_short():
+    """A dozen scenes of tests/fuzz_slabs.py (the full campaign of round 2: 5362 scenes, 33 M rays, no mismatch)."""
+    import fuzz_slabs
+    assert fuzz_slabs.campaign(seed=20261018, seconds=120.0, max_scenes=12, quiet=True) == 12
