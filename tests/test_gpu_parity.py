@@ -487,6 +487,51 @@ def test_child_slabs_around_the_tame_boundary_bit_exact(gpu_ctx):
     assert (ref["accum"].reshape(-1, 3) != 0).any(1).sum() > 500, "the frame is meant to show the mesh"
 
 
+def test_culling_and_scheduler_fuzz_on_random_scenes(gpu_ctx):
+    """Random scenes of the kinds of tests/fuzz_slabs.py with random materials, on the device: `k_intersect_batch` on aimed,
+    tame-boundary and adversarial rays, and a small frame through `k_primary` + `k_paths_pool` (queues, flattened leaf phase,
+    filter, child slabs) -- hits, accumulation buffer and RGB8 equal the oracle's bit for bit."""
+    import fuzz_slabs
+    from common import tame_boundary_rays
+    rng = np.random.default_rng(31337)
+    fuzz_slabs.rng = rng
+    cam = default_cam()
+    lit = 0
+    for case in range(8):
+        kind = case % 5
+        n = int(rng.choice([300, 3000, 12000]))
+        v9, mi, mats = fuzz_slabs.rand_scene(kind, n)
+        if case < 5:                                         # keep the generator's own scale for the ray tests
+            osc, hs = build_pair(v9, mi, mats)
+            gpu_ctx.upload(hs)
+            pts = v9.reshape(-1, 3); lo, hi = pts.min(0), pts.max(0); c = 0.5 * (lo + hi); h = 0.5 * (hi - lo) + 1e-6
+            m = 40_000
+            org = (c + rng.uniform(-2.2, 2.2, (m, 3)) * h).astype(np.float32)
+            tgt = pts[rng.integers(0, len(pts), m)] + rng.normal(size=(m, 3)) * h * 0.01
+            d = tgt - org; d /= np.linalg.norm(d, axis=1, keepdims=True) + 1e-30
+            d = (d * rng.choice([1.0, 1.0, 0.5, 1.15], (m, 1))).astype(np.float32)
+            o2, d2 = tame_boundary_rays(v9, 4000, seed=case)
+            o3, d3 = adversarial_rays(v9, seed=case, n_each=64)
+            O_ = np.concatenate([org, o2, o3]); D_ = np.concatenate([d, d2, d3])
+            assert_same_hits(gpu_ctx.intersect_batch(O_, D_), osc.intersect_batch(O_, D_), "fuzz scene %d (kind %d)" % (case, kind))
+        v9 = (v9.reshape(-1, 3) * np.float32(1.5 / max(1e-6, float(np.abs(v9).max())))).reshape(n, 9)     # into the camera's view
+        nm = 6
+        mats = np.zeros((nm, 8), np.float32)
+        mats[:, 0] = rng.choice([0.0, 0.3, 1.0], nm); mats[:, 1:4] = rng.uniform(0, 1, (nm, 3))
+        mats[:, 4] = rng.choice([0.0, 0.0, 2.0, 10.0], nm); mats[:, 5:8] = rng.uniform(0, 1, (nm, 3))
+        mats[0, 4] = 5.0
+        mi = rng.integers(0, nm, n).astype(np.int32)
+        osc, hs = build_pair(v9, mi, mats)
+        gpu_ctx.upload(hs)
+        depth = int(rng.choice([3, 8])); spp = int(rng.choice([4, 9]))
+        seed = int(rng.integers(1000))
+        out = gpu_ctx.render(cam, pysqt.make_params(160, 120, spp, max_depth=depth, seed=seed))
+        ref = osc.render(cam, O.make_params(160, 120, spp, max_depth=depth, seed=seed, trig=1))
+        assert np.array_equal(bits(out["accum"]), bits(ref["accum"])) and np.array_equal(out["rgb8"], ref["rgb8"]), "fuzz frame %d" % case
+        lit += int((ref["accum"] != 0).any())
+    assert lit >= 4, "most frames are meant to show lit geometry"
+
+
 def default_cam():
     return pysqt.load_camera(pysqt.ROOT + "/data/camera")
 
