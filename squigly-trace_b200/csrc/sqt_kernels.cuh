@@ -261,17 +261,20 @@ __global__ void __launch_bounds__(128, SQT_WL_MIN_BLOCKS) k_paths(SceneView sc, 
 // ------------------------------------------------------------------------------ ray pools
 // k_paths_pool: the same per-ray logic as k_paths, scheduled differently.  Every warp owns a POOL of P = 32*K rays whose
 // state lives in shared memory (structure of arrays, 16 words per ray; traversal stacks, per-path material lists and the
-// integrator state of a slot in global memory, one region per pool slot).  A ray waits in one of three queues (rings of
-// slot ids in shared memory, appended to with a ballot + popc at write-back, so there is no census and no gather):
+// integrator state of a slot in global memory, one region per pool slot).  A ray waits in one of four queues (byte rings of
+// slot ids in shared memory, heads and fills packed in two warp-uniform registers; a served ray is appended with one MATCH + one
+// packed REDUX at write-back, so there is no census and no gather):
 //   T  traversal steps (ST_DESC): a short burst of branch visits; the ray's interval and child travel in registers, its
-//      origin / direction components are read from the pool by split axis (PoolRay)
+//      origin / direction components are read from the pool by split axis (PoolRayS)
 //   L  leaf work (ST_ENTER / ST_LEAF): every gathered ray enters its leaf (record fetch + conservative culling), then the
 //      (ray, triangle) tests of ALL gathered rays are laid out consecutively and executed 32 per step, one test per lane,
 //      whichever lane gathered the ray -- any lane can read any ray from the pool -- and accepted hits are folded into
 //      the owning ray's best hit in test order (from the leaf's last triangle to its first: BIH.hs:105-109, minimumBy =
-//      foldr1 min'); leaves are always worked off to completion, so a ray leaves this queue as ST_RET
+//      foldr1 min'); a test first passes a division-free filter for the `a` / `u` guards, the survivors are re-run in full,
+//      32 at a time; then the stack is popped right there with all gathered lanes (ret_step)
 //   R  regeneration (ST_DONE): consume the hit, shade, bounce or fetch the next sample, start the ray (staged for all
 //      gathered lanes at once, path_regen_warp)
+//   S  (extension) fold the analytic spheres into the BIH result (ST_SPH)
 // Each round the warp serves the longest queue with up to 32 lanes.  With one ray per lane at most ~10 of 32 lanes share a
 // step kind at any time (tests/sched_sim.py); regrouping rays lifts that limit.  Scheduling never changes a result: every
 // ray runs the same unit steps of sqt_core.cuh in the same order (test_every_path_kernel_scheduler_is_bit_exact).
@@ -308,7 +311,7 @@ struct PoolRayS {
 // c_min: serve the regeneration queue only when it holds at least this many rays (or nothing else can run)
 struct PoolTune { int burst_t, t_leave, c_min; };
 
-// 16 words = 64 B per ray in shared memory; the first nine are what PoolRay reads.  PF_TMIN holds the interval's lower
+// 16 words = 64 B per ray in shared memory; the first nine are what PoolRayS reads.  PF_TMIN holds the interval's lower
 // end while the ray descends and `i` (triangles left - 1) for a ray that starts inside a leaf (root leaf);
 // PF_FLAGS = TravLane::rf (bits 0-2, 27, 30) | state << 4 | sp << 8.
 enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_DFX, PF_DFY, PF_DFZ, PF_CHILD, PF_TMIN, PF_TMAX, PF_CTRI, PF_CT, PF_CDIST,
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(128, SQT_POOL_MIN_BLOCKS) k_paths_pool(SceneVi
     constexpr int P = 32 * K;                     // rays per warp (a power of two)
     constexpr int PT = 4 * P;                     // pool slots of the CTA: slot g = warp * P + s, and g is what the queues hold,
                                                   // so the hot accesses index CTA-wide arrays by a value the lane already has
-                                                  // (no per-warp base address to rematerialise)
+                                                  // (one uniform base, see lds32)
     // per-warp scratch, kept small on purpose: 8 CTAs x (pool + scratch + 1 KB) must stay within the 164 KB shared-memory
     // carve-out, the next one (196 KB) would leave 32 KB instead of 64 KB of L1 for triangles, nodes and stacks
     constexpr int AUX_WORDS = 4 * P / 4 + 64 + 8 + 8 + 32;
