@@ -2,7 +2,7 @@
 anisotropic extent, thin bumpy sheets, needles that cross the whole box, coordinates around 1000, a 0.02-sized scene) x rays aimed at
 the geometry, the tame-boundary set and the adversarial set; the host build of the device code (tests/emu, culling on, plain and
 interleaved-pool layout) must return the oracle's hits bit for bit.
-usage: python tests/fuzz_slabs.py SEED SECONDS     (round 2: seeds 1-4 x 600 s = 5362 scenes, 33 M rays, no mismatch)
+usage: python tests/fuzz_slabs.py SEED SECONDS     (round 2: seeds 1-4 x 600 s and 21-26 x 1200 s = 18 122 scenes, 110 M rays, no mismatch)
 tests/test_emu_parity.py::test_culling_fuzz_short runs a dozen scenes of it."""
 import os
 import sys, time
